@@ -1,0 +1,138 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(/root/reference/textSeqCompare.py) in the build container.
+
+    python tests/golden/make_golden.py            # ~1-2 min (two full pages at ~18 s each)
+
+The reference cannot travel to the GPU box, so its outputs are committed as small JSON
+fixtures.  Each record carries the inputs, the scoring system, the aligned sequences as an
+op string ('0' diag, '1' transcript char vs '_', '2' '_' vs OCR char), the end-corner scores
+(M, X, Y)[n][m] (NEG = -1e100 -> null) and a sha256 of the packed pointer matrix
+(PM | PX<<2 | PY<<4)[1:,1:] captured from the reference's own np.zeros arrays.
+"""
+import hashlib
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle import ref_loader          # noqa: E402
+from text_alignment_b200 import synth  # noqa: E402
+import scorers                         # noqa: E402
+
+
+def ops_from_alignment(tra, ocr):
+    out = []
+    for a, b in zip(tra, ocr):
+        if b == '_' and a != '_':
+            out.append('1')
+        elif a == '_' and b != '_':
+            out.append('2')
+        else:
+            out.append('0')
+    return ''.join(out)
+
+
+def run_ref(T, O, system):
+    """T, O lists; system a reference-style scoring list (callable given by name)."""
+    sysobj = system
+    if system is not None and isinstance(system[0], str):
+        sysobj = [scorers.SCORERS[system[0]]] + list(system[1:])
+    tra, ocr, mats = ref_loader.reference_align_full(T, O, sysobj)
+    n, m = len(T), len(O)
+    # op string is unambiguous only if the inputs contain no '_' (true for all fixtures)
+    ops = ops_from_alignment(tra, ocr)
+    assert len(tra) == len(ocr)
+    ptr = (mats['PM'].astype(np.uint8) | (mats['PX'].astype(np.uint8) << 2) |
+           (mats['PY'].astype(np.uint8) << 4))[1:, 1:]
+    end = [mats[k][n][m] for k in ('M', 'X', 'Y')]
+    end = [None if v <= -1e99 else (int(v) if float(v).is_integer() else float(v)) for v in end]
+    return dict(ops=ops, end=end, ptr_sha256=hashlib.sha256(np.ascontiguousarray(ptr).tobytes()).hexdigest(),
+                tra=tra, ocr=ocr)
+
+
+def main():
+    # ---- 1. known-answer tests -------------------------------------
+    kat_pairs = [('abc', 'abc'), ('abc', ''), ('', 'abc'), ('', ''), ('a', 'b'), ('ab', 'ba'),
+                 ('dominus', 'dns'), ('dns', 'dominus'), ('alleluia', 'a l l e l u y a'),
+                 ('gloria', 'xxxxgloriaxxxx'), ('xxxxgloriaxxxx', 'gloria'),
+                 ('ca', 'aa'), ('a', 'a'), ('a', 'c')]
+    kats = []
+    for t, o in kat_pairs:
+        r = run_ref(list(t), list(o), None)
+        kats.append(dict(T=t, O=o, system=None, ops=r['ops'], end=r['end'], ptr_sha256=r['ptr_sha256'],
+                         tra=''.join(r['tra']), ocr=''.join(r['ocr'])))
+    for t, o, s in [('aaaa', 'aa', [10, -5, -7, -7]), ('abcabc', 'abc', [5, -4, -2, -7, 0, -5])]:
+        r = run_ref(list(t), list(o), s)
+        kats.append(dict(T=t, O=o, system=s, ops=r['ops'], end=r['end'], ptr_sha256=r['ptr_sha256'],
+                         tra=''.join(r['tra']), ocr=''.join(r['ocr'])))
+    # the reference's own demo (textSeqCompare.py:180-190): 2-char elements, 4-parameter system
+    seq1 = 'Lorem ipsum dolor sit amet, consectetur adipiscing elit '
+    seq2 = 'LoLorem fipsudolor ..... sit eamet, c.nnr adizisdcing eelitellit'
+    e1 = [seq1[2 * x] + seq1[2 * x + 1] for x in range(len(seq1) // 2)]
+    e2 = [seq2[2 * x] + seq2[2 * x + 1] for x in range(len(seq2) // 2)]
+    r = run_ref(e1, e2, [10, -5, -7, -7])
+    demo = dict(T=e1, O=e2, system=[10, -5, -7, -7], ops=r['ops'], end=r['end'], ptr_sha256=r['ptr_sha256'],
+                tra='|'.join(r['tra']), ocr='|'.join(r['ocr']))
+    r = run_ref(list(seq1), list(seq2), None)
+    demo_chars = dict(T=seq1, O=seq2, system=None, ops=r['ops'], end=r['end'], ptr_sha256=r['ptr_sha256'],
+                      tra=''.join(r['tra']), ocr=''.join(r['ocr']))
+    json.dump(dict(kats=kats, demo=demo, demo_chars=demo_chars), open(os.path.join(HERE, 'kats.json'), 'w'),
+              indent=1, sort_keys=True)
+
+    # ---- 2. random differential vectors ------------------------------------------------------
+    rng = random.Random(20261018)
+    rnd = []
+    systems = [None, [10, -5, -7, -7], [5, -4, -2, -7, 0, -5], [8, -4, -7, -7, -3, 0],
+               [1, -1, -1, -1], [3, -2, 0, 0, -1, -1], [2, 2, -1, -3, -2, 0], [0, 0, 0, 0],
+               [7, -3, -4, -9, -1, -2], [11, -10, -2, -2, -5, -5], [5, -7, -7, -2, 0, -3],
+               [1, 3, -2, -2, -1, -1], [4, -4, 2, -3, -1, 1],
+               ['vowel_aware', -7, -7, -3, 0], ['confusable', -4, -6, -1, -2], ['asymmetric', -3, -3, -1, -1]]
+    for k in range(420):
+        alpha = rng.choice(['ab', 'abc', 'acgt', 'aeioudnm s', 'abcdefghilmnopqrstuvxy .'])
+        n = rng.randint(0, 34) if k % 7 else rng.randint(0, 3)
+        m = rng.randint(0, 34) if k % 5 else rng.randint(0, 3)
+        t = ''.join(rng.choice(alpha) for _ in range(n))
+        if rng.random() < 0.5 and n:
+            # OCR-like derivative so that long matching diagonals and ties both occur
+            o = synth.gen_ocr(rng, t, 0.25, 0.2, m, 1, 4)[:m] if m else ''
+        else:
+            o = ''.join(rng.choice(alpha) for _ in range(m))
+        s = systems[k % len(systems)] if k % 3 else (
+            [rng.randint(0, 12), rng.randint(-10, 2)] + [rng.randint(-10, 1) for _ in range(4)])
+        r = run_ref(list(t), list(o), s)
+        rnd.append(dict(T=t, O=o, system=s, ops=r['ops'], end=r['end'], ptr_sha256=r['ptr_sha256']))
+    # medium pairs (a few strips wide for the GPU kernel; several hundred columns)
+    for k, (n, m, runs) in enumerate([(150, 200, (2, 8)), (200, 150, (2, 8)), (97, 333, (10, 60)),
+                                      (260, 130, (1, 3)), (129, 257, (3, 20)), (64, 1025, (50, 200))]):
+        t, o = synth.make_pair(7000 + k, n, m, *runs)
+        s = [None, [10, -5, -7, -7], [5, -4, -2, -7, 0, -5], None, ['vowel_aware', -7, -7, -3, 0], None][k]
+        r = run_ref(list(t), list(o), s)
+        rnd.append(dict(T=t, O=o, system=s, ops=r['ops'], end=r['end'], ptr_sha256=r['ptr_sha256']))
+    json.dump(rnd, open(os.path.join(HERE, 'random_pairs.json'), 'w'), indent=0)
+
+    # ---- 3. the Appendix C seeded vectors (inputs regenerated from the seed; digests only) -----
+    app = []
+    for tag, seed, n, m, lo, hi in [('salzinnes_page', 1001, 1200, 1500, 5, 40),
+                                    ('stgall_page', 1002, 800, 2400, 50, 400),
+                                    ('line_pair', 1003, 80, 100, 2, 6)]:
+        t, o = synth.make_pair(seed, n, m, lo, hi)
+        r = run_ref(list(t), list(o), None)
+        app.append(dict(tag=tag, seed=seed, n=n, m=m, run_lo=lo, run_hi=hi,
+                        input_sha256=hashlib.sha256((t + '\n' + o).encode()).hexdigest(),
+                        align_sha256=hashlib.sha256((''.join(r['tra']) + '\n' + ''.join(r['ocr'])).encode()).hexdigest(),
+                        ptr_sha256=r['ptr_sha256'], end=r['end'], L=len(r['ops']),
+                        gaps_tra=r['tra'].count('_'), gaps_ocr=r['ocr'].count('_'),
+                        ops_sha256=hashlib.sha256(r['ops'].encode()).hexdigest()))
+        print(tag, app[-1]['end'], app[-1]['L'], app[-1]['align_sha256'])
+    json.dump(app, open(os.path.join(HERE, 'appendix_c.json'), 'w'), indent=1, sort_keys=True)
+
+
+if __name__ == '__main__':
+    main()
