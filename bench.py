@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the affine-gap NW hot path (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c3|c4] [--pairs P]
+
+A "step" is one pass of the hot path over one batch: `--pairs` synthetic pairs of the chosen
+BASELINE config per GPU (default config 2: 10 000 seeded page pairs of 1-2k characters;
+SURVEY.md 8(d)), default scoring [8,-4,-7,-7,-3,0].  Weak scaling: every rank aligns its own
+batch, no data-path collective (pairs are independent).
+
+  value  : whole-job GCUPS (sum over ranks of n*m / max-over-ranks device time), inputs
+           resident in HBM, timed with CUDA events on the library's stream;
+  e2e    : the same metric through the C-ABI call tanw_align_batch with pinned HOST buffers:
+           H2D of symbols + pair table, fill, traceback, D2H of op strings / lengths / scores
+           inside the timed region;
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+`--impl reference` times the CPU restatement of the reference's pure-Python aligner
+(oracle/py_port.py; the reference itself, being Python, cannot travel to the GPU box) over
+all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_CELL = 21          # algorithmic int32 ops per cell of the reference recurrence
+PTR_BYTES_PER_CELL = 1     # three 2-bit pointers packed in one byte
+DEFAULT_PARAMS = (8, -4, -7, -7, -3, 0, -1)
+NOMINAL_INT32_PEAK = 148 * 64 * 1.965e9     # alu pipe, lane-ops/s
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get('hbm_gbs', 6650.0)), 'measured'
+    return 6650.0, 'fallback'
+
+
+# ---- workload ---------------------------------------------------------------------------------
+
+def _gen_one(args):
+    from text_alignment_b200 import synth
+    which, k = args
+    return getattr(synth, which + '_pair')(k)
+
+
+def make_workload(which, first, count, procs):
+    """Seeded pairs `first .. first+count` of a BASELINE config, packed for the C ABI."""
+    jobs = [(which, first + k) for k in range(count)]
+    if procs > 1 and count >= 64:
+        with mp.get_context('fork').Pool(procs) as pool:
+            pairs = pool.map(_gen_one, jobs, chunksize=max(1, count // (procs * 8)))
+    else:
+        pairs = [_gen_one(j) for j in jobs]
+    return pack_pairs(pairs), pairs
+
+
+def pack_pairs(pairs):
+    n = np.array([len(t) for t, _ in pairs], dtype=np.int32)
+    m = np.array([len(o) for _, o in pairs], dtype=np.int32)
+    buf = np.frombuffer(''.join(t + o for t, o in pairs).encode('latin-1'), dtype=np.uint8).copy()
+    lens = n.astype(np.int64) + m
+    t_off = np.zeros(len(pairs), dtype=np.int64)
+    if len(pairs):
+        np.cumsum(lens[:-1], out=t_off[1:])
+    return buf, t_off, n, t_off + n, m
+
+
+WORKLOADS = {
+    'c2': dict(name='config 2: seeded synthetic page pairs, n~U[1000,1600], m=1.25n, 20% sub + 5% indel, runs 5-40',
+               default_pairs=10000),
+    'c3': dict(name='config 3: seeded synthetic line pairs, n,m~U[40,120], runs 2-6', default_pairs=200000),
+    'c4': dict(name='config 4: St. Gall-shaped pages, n~U[600,1000], m=n*U[2,4], inserted runs 50-400',
+               default_pairs=4096),
+}
+
+
+# ---- clocks ----------------------------------------------------------------------------------
+
+class ClockSampler(object):
+    """nvidia-smi sampling DURING the timed region (profiling recipe's clocks line)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            inside = t0 <= ts <= t1 + 0.1
+            try:
+                if inside:
+                    sm.append(float(f[1])); power.append(float(f[3]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            if inside:
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        if not sm:      # region shorter than the sampling period: use every sample we have
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(',')]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=max(smax) if smax else None,
+                    power_w_max=max(power) if power else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# ---- CPU baseline (oracle: the only place bench.py may execute oracle/) -------------------------
+
+def _py_port_one(args):
+    from oracle import py_port
+    t, o = args
+    t0 = time.perf_counter()
+    py_port.perform_alignment(list(t), list(o))
+    return len(t) * len(o), time.perf_counter() - t0
+
+
+def crop_pairs(pairs, cells_per_pair):
+    out = []
+    for t, o in pairs:
+        f = min(1.0, (cells_per_pair / max(1.0, float(len(t)) * len(o))) ** 0.5)
+        out.append((t[:max(1, int(len(t) * f))], o[:max(1, int(len(o) * f))]))
+    return out
+
+
+def cpu_python_port(pairs, cores, target_s):
+    """The reference's algorithm in pure Python (oracle/py_port.py, ~10 us per cell like the
+    reference), one pair per host core, pairs cropped so a step lasts about target_s."""
+    sample = crop_pairs(pairs[:cores], target_s / 10e-6)
+    t0 = time.perf_counter()
+    with mp.get_context('fork').Pool(cores) as pool:
+        res = pool.map(_py_port_one, sample, chunksize=1)
+    wall = time.perf_counter() - t0
+    cells = sum(c for c, _ in res)
+    return cells, wall, sample
+
+
+def cpu_c_oracle(packed, cores, max_pairs):
+    from oracle import nw_oracle
+    buf, t_off, n, o_off, m = packed
+    k = min(max_pairs, n.size)
+    sc, _ = nw_oracle.make_scoring(list(DEFAULT_PARAMS[:6]), boundary_gap=DEFAULT_PARAMS[6])
+    t0 = time.perf_counter()
+    nw_oracle.align_batch_codes(buf, t_off[:k], n[:k], o_off[:k], m[:k], sc, threads=cores, want_scores=False)
+    wall = time.perf_counter() - t0
+    cells = int((n[:k].astype(np.int64) * m[:k]).sum())
+    return cells, wall, k
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0))
+    wl = WORKLOADS[args.workload]
+    _, pairs = make_workload(args.workload, 0, cores, min(cores, 16))
+    total = args.steps + args.warmup
+    target_s = max(0.5, min(20.0, 150.0 / max(total, 1)))
+    for _ in range(args.warmup):
+        cpu_python_port(pairs, cores, target_s)
+    cells = 0
+    wall = 0.0
+    sample = None
+    for _ in range(args.steps):
+        c, w, sample = cpu_python_port(pairs, cores, target_s)
+        cells += c
+        wall += w
+    gcups = cells / wall / 1e9
+    desc = ('%d crops of %s pages per step (first ~%dx%d chars of seeds 2000000..), one per host core, '
+            'pure-Python restatement of textSeqCompare.py (oracle/py_port.py); the reference is Python and '
+            'cannot travel to the GPU box' % (len(sample), args.workload, len(sample[0][0]), len(sample[0][1])))
+    line = dict(impl='reference', metric='affine_nw_gcups', value=gcups, unit='GCUPS', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=wall / max(args.steps, 1) * 1e3,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64 (python float)', data='synthetic',
+                config=dict(workload=wl['name'], scoring=list(DEFAULT_PARAMS[:6])),
+                pages_per_s=len(sample) * args.steps / wall,
+                cpu_baseline=dict(value=gcups, unit='GCUPS', cores=cores, kind='port', sample=desc),
+                e2e=dict(value=gcups, unit='GCUPS', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+    return 0
+
+
+# ---- our arm ---------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU per step (default: the config size)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parity-pairs', type=int, default=16)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from text_alignment_b200 import _native
+    from text_alignment_b200.textSeqCompare import get_context
+
+    wl = WORKLOADS[args.workload]
+    npairs = args.pairs or wl['default_pairs']
+    cores = len(os.sched_getaffinity(0))
+    gen_procs = max(1, min(32, cores // max(world, 1)))
+    packed, pairs = make_workload(args.workload, rank * npairs, npairs, gen_procs)
+    buf, t_off, n, o_off, m = packed
+    cells = int((n.astype(np.int64) * m).sum())
+
+    ctx = get_context(local_rank)
+    scoring = ctx.make_scoring(*DEFAULT_PARAMS)
+
+    # ---- parity spot check against the oracle (outside every timed region) ----------------------
+    parity = 0
+    if args.parity_pairs > 0:
+        from oracle import nw_oracle
+        k = min(args.parity_pairs, npairs)
+        sub = pack_pairs(pairs[:k])
+        got = ctx.align_batch(*sub, scoring)
+        sc, _ = nw_oracle.make_scoring(list(DEFAULT_PARAMS[:6]), boundary_gap=DEFAULT_PARAMS[6])
+        want = nw_oracle.align_batch_codes(*sub, sc, threads=min(cores, 16))
+        ok = np.array_equal(got[2], want[2]) and all(
+            np.array_equal(got[0][got[1][i]:got[1][i] + got[2][i]], want[0][want[1][i]:want[1][i] + want[2][i]])
+            for i in range(k))
+        ok = ok and np.array_equal(got[3].astype(np.float64), np.where(want[3] <= -1e99, _native.NEG_INF, want[3]))
+        if not ok:
+            print(json.dumps(dict(error='parity check against the oracle FAILED; no number reported')))
+            return 2
+        parity = k
+
+    # ---- pinned host buffers for the end-to-end leg ------------------------------------------------
+    def pinned(a):
+        t = torch.empty(max(a.size, 1), dtype=torch.uint8, pin_memory=True)
+        v = t.numpy()[:a.size]
+        v[...] = a
+        return t, v
+    keep = []
+    p_buf = pinned(buf); keep.append(p_buf)
+    ops_cap = int((n.astype(np.int64) + m).sum())
+    t_ops = torch.empty(max(ops_cap, 1), dtype=torch.uint8, pin_memory=True)
+    t_len = torch.empty(max(npairs, 1), dtype=torch.int32, pin_memory=True)
+    t_sc = torch.empty((max(npairs, 1), 3), dtype=torch.int32, pin_memory=True)
+    out = (t_ops.numpy(), t_len.numpy(), t_sc.numpy())
+
+    ext = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device('cuda', local_rank))
+    int32_peak = max(ctx.measure_int32_peak(0), ctx.measure_int32_peak(1))
+    int32_fused = ctx.measure_int32_peak(2)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: inputs resident in HBM, K launches back to back, CUDA events on the lib stream ----
+    ctx.prepare(p_buf[1], t_off, n, o_off, m, scoring)
+    for _ in range(args.warmup):
+        ctx.run()
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record(ext)
+    for _ in range(args.steps):
+        ctx.run()
+    e1.record(ext)
+    ctx.sync()
+    barrier()
+    w1 = time.perf_counter()
+    dev_ms = e0.elapsed_time(e1)
+    launches = args.steps * ctx.timing()['kernel_launches']
+
+    # ---- leg 2: end to end through the C ABI with host buffers ------------------------------------
+    for _ in range(2):
+        ctx.align_batch(p_buf[1], t_off, n, o_off, m, scoring, out=out)
+    barrier()
+    x0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.align_batch(p_buf[1], t_off, n, o_off, m, scoring, out=out)
+    barrier()
+    x1 = time.perf_counter()
+    tm = ctx.timing()
+    clocks = sampler.stop(w0, x1)
+    e2e_s = x1 - x0
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s * 1e3, w1 - w0], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, wall_s = t.tolist()
+        c = torch.tensor([cells, npairs], dtype=torch.float64, device='cuda')
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tot_cells, tot_pairs = c.tolist()
+    else:
+        e2e_ms, wall_s, tot_cells, tot_pairs = e2e_s * 1e3, w1 - w0, float(cells), float(npairs)
+
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        gcups = tot_cells * args.steps / (dev_ms * 1e-3) / 1e9
+        e2e_gcups = tot_cells * args.steps / (e2e_ms * 1e-3) / 1e9
+        launch_s = dev_ms * 1e-3 / args.steps                     # one launch per step on this rank
+        ach_ops = cells * OPS_PER_CELL / launch_s
+        ach_gbs = cells * PTR_BYTES_PER_CELL / launch_s / 1e9
+        line = dict(
+            metric='affine_nw_gcups', value=gcups, unit='GCUPS', n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='weak',
+            vs_baseline=None, dtype='int32', data='synthetic',
+            config=dict(workload=wl['name'], pairs_per_gpu=npairs, cells_per_gpu=cells,
+                        scoring=list(DEFAULT_PARAMS[:6]), parallelism='pairs sharded, %d rank(s)' % world,
+                        l2='every step writes %d MB of traceback pointers per GPU (>> 126 MB L2)' % (cells // 2 ** 20),
+                        parity_checked_pairs=parity),
+            pages_per_s=tot_pairs * args.steps / (dev_ms * 1e-3),
+            wall_ms_per_step=wall_s * 1e3 / args.steps,
+            e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=int(tm['h2d_bytes']),
+                     d2h_bytes_per_step=int(tm['d2h_bytes']), pages_per_s=tot_pairs * args.steps / (e2e_ms * 1e-3),
+                     ms_per_step=e2e_ms / args.steps,
+                     breakdown_ms=dict(h2d=tm['h2d_ms'], kernel=tm['kernel_ms'], d2h=tm['d2h_ms'])),
+            gpu_launches=launches,
+            roofline=dict(bound='alu', achieved=ach_ops / 1e12, peak=int32_peak / 1e12, unit='Tlane-op/s',
+                          frac=ach_ops / int32_peak, traffic=None,
+                          note='%d algorithmic int32 ops/cell (SURVEY 8(d)) / measured IADD-VIMNMX issue peak; '
+                               'nominal alu-pipe peak %.1f' % (OPS_PER_CELL, NOMINAL_INT32_PEAK / 1e12),
+                          fused_peak=int32_fused / 1e12,
+                          hbm=dict(bound='hbm', achieved=ach_gbs, peak=hbm_peak, unit='GB/s',
+                                   frac=ach_gbs / hbm_peak, peak_source=hbm_src)),
+            clocks=clocks)
+        if not args.no_cpu_baseline:
+            t_s = 12.0
+            c_cells, c_wall, sample = cpu_python_port(pairs, cores, t_s)
+            line['cpu_baseline'] = dict(
+                value=c_cells / c_wall / 1e9, unit='GCUPS', cores=cores, kind='port',
+                sample='%d crops (~%dx%d chars) of the same pages, one per host core, pure-Python restatement '
+                       'of textSeqCompare.py (oracle/py_port.py)' % (len(sample), len(sample[0][0]), len(sample[0][1])))
+            k_cells, k_wall, k = cpu_c_oracle(packed, cores, max(cores * 4, 64))
+            line['cpu_baseline_c'] = dict(value=k_cells / k_wall / 1e9, unit='GCUPS', cores=cores, kind='port',
+                                          sample='%d full pages, oracle/nw_oracle.c (scalar C, float64), %d threads' % (k, cores))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,144 @@
+/*
+ * tanw.h -- C ABI of libtanw.so: batched affine-gap Needleman-Wunsch (three-matrix Gotoh
+ * form with the reference's exact tie-breaks) on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of DDMAL/text_alignment:
+ *     textSeqCompare.perform_alignment(transcript, ocr, scoring_system, verbose)
+ *     /root/reference/textSeqCompare.py:13-177, called from alignToOCR.py:273-274.
+ * The Python module text_alignment_b200/textSeqCompare.py keeps that signature and calls the
+ * functions below through ctypes.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a TANW_E_* code otherwise; the message is
+ *     available from tanw_last_error(ctx) (or tanw_last_error(NULL) for create failures);
+ *   - the caller owns every host buffer and keeps it alive for the duration of the call;
+ *     the library owns device memory, streams and staging inside the context;
+ *   - a context is single-caller; distinct contexts (one per GPU) may be driven from
+ *     distinct host threads concurrently (that is the multi-GPU model);
+ *   - there is no CPU fallback: without an sm_100 device tanw_create fails.
+ *
+ * Data model (replaces the Python lists of textSeqCompare.py:13, :21-22)
+ *   symbols : uint8 codes, all sequences of the batch concatenated; equal codes <=> elements
+ *             that compare equal in Python (the shim interns them per pair);
+ *   pair p  : transcript = symbols[t_off[p] .. t_off[p]+n[p]), OCR = symbols[o_off[p] .. +m[p]);
+ *   ops     : per pair, the alignment columns left to right, one byte per column:
+ *             0 = (T[x], O[y])  diagonal          (textSeqCompare.py:115-125)
+ *             1 = (T[x], '_')   gap in the OCR     (textSeqCompare.py:128-135, :160-164)
+ *             2 = ('_', O[y])   gap in transcript  (textSeqCompare.py:138-145, :154-158)
+ *             written at ops[ops_off[p] .. ops_off[p]+ops_len[p]); capacity n[p]+m[p];
+ *   scores  : (M, X, Y)[n][m] per pair as int32 (the reference keeps them in mat / x_mat /
+ *             y_mat, textSeqCompare.py:45-47, and returns none); TANW_NEG_INF stands for the
+ *             reference's -1e100 sentinel (:55, :60).
+ */
+#ifndef TANW_H
+#define TANW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TANW_OK            0
+#define TANW_E_INVALID     1   /* bad argument (null pointer, negative size, ...)            */
+#define TANW_E_RANGE       2   /* scores would not fit the int32 fixed-point representation   */
+#define TANW_E_CUDA        3   /* a CUDA runtime call failed                                  */
+#define TANW_E_NODEVICE    4   /* no sm_100 device / device index out of range                */
+#define TANW_E_NOMEM       5   /* host or device allocation failed                            */
+#define TANW_E_STATE       6   /* call order violated (run before prepare, ...)               */
+
+#define TANW_NEG_INF       (-1073741824)   /* int32 stand-in for -1e100 in score outputs */
+
+typedef struct tanw_ctx tanw_ctx;
+
+/* Scoring system after the parsing of textSeqCompare.py:24-42.
+ * subst == NULL : score(a,b) = (a == b) ? match : mismatch      (:31-32, :36-37)
+ * subst != NULL : score(a,b) = subst[a*subst_k + b], the tabulated user callable (:27-29);
+ *                 every symbol code in the batch must be < subst_k (<= 256).
+ * boundary_gap  : the module-level constant gap_extend that initialises row 0 / column 0
+ *                 (:9, :54-59) -- NOT the call's gap parameters. */
+typedef struct tanw_scoring {
+    int32_t match;
+    int32_t mismatch;
+    int32_t gap_open_x;
+    int32_t gap_open_y;
+    int32_t gap_extend_x;
+    int32_t gap_extend_y;
+    int32_t boundary_gap;
+    int32_t subst_k;
+    const int32_t *subst;
+} tanw_scoring;
+
+typedef struct tanw_device_info {
+    char     name[128];
+    int32_t  cc_major, cc_minor;
+    int32_t  sm_count;
+    int32_t  clock_khz;
+    int64_t  total_mem_bytes;
+    int64_t  free_mem_bytes;
+} tanw_device_info;
+
+/* CUDA-event timings of the most recent batch on this context, milliseconds. */
+typedef struct tanw_timing {
+    float   h2d_ms;        /* prepare: host -> device copies of symbols + pair table           */
+    float   kernel_ms;     /* run: fill + traceback kernels                                    */
+    float   d2h_ms;        /* fetch: device -> host copies of ops, lengths, scores             */
+    int32_t kernel_launches;  /* kernels launched by run                                       */
+    int64_t cells;         /* sum of n*m over the batch                                        */
+    int64_t ptr_bytes;     /* traceback-pointer bytes the fill kernel writes (algorithmic)     */
+    int64_t h2d_bytes, d2h_bytes;
+} tanw_timing;
+
+/* ---- library / device queries ------------------------------------------------------------ */
+int  tanw_version(void);                                  /* 100*major + minor                 */
+int  tanw_device_count(int *count);
+int  tanw_device_query(int device, tanw_device_info *out);
+const char *tanw_last_error(const tanw_ctx *ctx);         /* ctx may be NULL                    */
+
+/* ---- context -------------------------------------------------------------------------------- */
+int  tanw_create(int device, tanw_ctx **out);
+int  tanw_destroy(tanw_ctx *ctx);
+/* Upper bound for the traceback-pointer arena in bytes (0 = default: 40% of device memory). */
+int  tanw_set_arena_limit(tanw_ctx *ctx, int64_t bytes);
+
+/* ---- one-call batch alignment: the entry the reference's call site maps to ------------------
+ * Replaces N calls of textSeqCompare.perform_alignment (textSeqCompare.py:13) -- copies the
+ * inputs to the device, runs fill + traceback, copies ops / lengths / scores back.
+ * scores may be NULL.  ops_off[p] must leave n[p]+m[p] bytes for pair p. */
+int  tanw_align_batch(tanw_ctx *ctx,
+                      const uint8_t *symbols, int64_t symbols_len,
+                      const int64_t *t_off, const int32_t *n,
+                      const int64_t *o_off, const int32_t *m,
+                      int64_t n_pairs, const tanw_scoring *scoring,
+                      uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
+                      int32_t *ops_len, int32_t *scores);
+
+/* ---- the same in three phases (bench.py times `run` alone with inputs resident in HBM) ------ */
+int  tanw_batch_prepare(tanw_ctx *ctx,
+                        const uint8_t *symbols, int64_t symbols_len,
+                        const int64_t *t_off, const int32_t *n,
+                        const int64_t *o_off, const int32_t *m,
+                        int64_t n_pairs, const tanw_scoring *scoring);
+int  tanw_batch_run(tanw_ctx *ctx);                       /* asynchronous on the ctx stream     */
+int  tanw_batch_fetch(tanw_ctx *ctx,
+                      uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
+                      int32_t *ops_len, int32_t *scores);
+int  tanw_sync(tanw_ctx *ctx);
+
+int  tanw_last_timing(tanw_ctx *ctx, tanw_timing *out);
+
+/* Raw CUDA stream of the context (cudaStream_t as an integer) so that a caller holding
+ * device memory of its own (e.g. torch) can order work against it. */
+int  tanw_stream_handle(tanw_ctx *ctx, uint64_t *out);
+
+/* ---- measurement helper: dependency-free int32 add/max throughput of this device ------------
+ * Measures the roofline denominator SURVEY.md 8(d) asks the builder to measure:
+ * lane-ops per second of IADD3 / VIMNMX issued from every SM.  `which`: 0 = add, 1 = max,
+ * 2 = fused add+max (VIADDMNMX counted as 2 ops). */
+int  tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TANW_H */

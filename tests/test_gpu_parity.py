@@ -1,0 +1,259 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the golden vectors of the
+unmodified reference and against the CPU oracle on seeded inputs.  Bit-exact: integer
+scores, op strings, aligned sequences.  Run on the B200 box with `-m gpu`."""
+import hashlib
+import io
+import random
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from conftest import golden_elems, ops_string, resolve_system
+from text_alignment_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def tsc():
+    from text_alignment_b200 import textSeqCompare
+    textSeqCompare.get_context(0)          # fails loudly without libtanw.so / a B200
+    return textSeqCompare
+
+
+@pytest.fixture(scope='module')
+def oracle():
+    from oracle import nw_oracle
+    return nw_oracle
+
+
+def _end(end):
+    return tuple(None if (v is None or v <= -1e99) else int(v) for v in end)
+
+
+def _pack(pairs):
+    buf = np.frombuffer(''.join(t + o for t, o in pairs).encode('latin-1'), dtype=np.uint8)
+    n = np.array([len(t) for t, _ in pairs], dtype=np.int32)
+    m = np.array([len(o) for _, o in pairs], dtype=np.int32)
+    lens = n.astype(np.int64) + m
+    t_off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64) if len(pairs) else np.zeros(0, np.int64)
+    return buf, t_off, n, t_off + n, m
+
+
+DEFAULT = (8, -4, -7, -7, -3, 0, -1)
+
+
+def _check_packed_vs_oracle(tsc, oracle, pairs, params=DEFAULT, threads=8):
+    buf, t_off, n, o_off, m = _pack(pairs)
+    ops, ops_off, ops_len, scores = tsc.align_packed(buf, t_off, n, o_off, m, params)
+    sc, _ = oracle.make_scoring(list(params[:6]), boundary_gap=params[6])
+    r_ops, r_off, r_len, r_end = oracle.align_batch_codes(buf, t_off, n, o_off, m, sc, threads=threads)
+    assert ops_len.tolist() == r_len.tolist()
+    assert ops_off.tolist() == r_off.tolist()
+    for k in range(len(pairs)):
+        a = ops[ops_off[k]:ops_off[k] + ops_len[k]]
+        b = r_ops[r_off[k]:r_off[k] + r_len[k]]
+        assert np.array_equal(a, b), 'pair %d (n=%d, m=%d): op strings differ' % (k, n[k], m[k])
+        want = _end(r_end[k].tolist())
+        got = tuple(None if v == -1073741824 else int(v) for v in scores[k].tolist())
+        assert got == want, 'pair %d: end scores %s vs %s' % (k, got, want)
+
+
+def test_kats_against_reference_golden(tsc, kats):
+    for rec in kats['kats'] + [kats['demo'], kats['demo_chars']]:
+        T, O = golden_elems(rec)
+        tra, ocr, score = tsc.perform_alignment(T, O, scoring_system=resolve_system(rec['system']),
+                                                return_scores=True)
+        sep = '|' if rec is kats['demo'] else ''
+        assert sep.join(tra) == rec['tra'] and sep.join(ocr) == rec['ocr'], (rec['T'], rec['O'])
+        assert tuple(score) == _end(rec['end'])
+
+
+def test_random_golden_pairs(tsc, random_pairs):
+    """436 vectors produced by the unmodified reference: all three scoring-system forms
+    (incl. callables), empty and ragged inputs, tie-heavy small alphabets."""
+    by_system = {}
+    for rec in random_pairs:
+        by_system.setdefault(repr(rec['system']), []).append(rec)
+    for recs in by_system.values():
+        system = resolve_system(recs[0]['system'])
+        pairs = [golden_elems(r) for r in recs]
+        out = tsc.perform_alignment_batch(pairs, scoring_system=system, return_scores=True)
+        for rec, (tra, ocr, score) in zip(recs, out):
+            assert ops_string(tra, ocr) == rec['ops'], (rec['T'], rec['O'], rec['system'])
+            assert tuple(score) == _end(rec['end']), (rec['T'], rec['O'], rec['system'])
+
+
+def test_appendix_c_pages(tsc, appendix_c):
+    """The three seeded page/line vectors of SURVEY.md Appendix C (digests from the reference)."""
+    for rec in appendix_c:
+        t, o = synth.make_pair(rec['seed'], rec['n'], rec['m'], rec['run_lo'], rec['run_hi'])
+        tra, ocr, score = tsc.perform_alignment(list(t), list(o), return_scores=True)
+        got = hashlib.sha256((''.join(tra) + '\n' + ''.join(ocr)).encode()).hexdigest()
+        assert got == rec['align_sha256'], rec['tag']
+        assert tuple(score) == _end(rec['end'])
+        assert len(tra) == rec['L'] and tra.count('_') == rec['gaps_tra'] and ocr.count('_') == rec['gaps_ocr']
+
+
+def test_quirk_discriminators(tsc):
+    """boundary constant, first-index tie-break, start state."""
+    assert tsc.perform_alignment(list('ca'), list('aa')) == (list('ca_'), list('_aa'))
+    assert tsc.perform_alignment(list('a'), list('a')) == (list('a'), list('a'))
+    assert tsc.perform_alignment(list('a'), list('c')) == (list('a'), list('c'))
+
+
+def test_module_gap_extend_read_at_call_time(tsc, oracle, monkeypatch):
+    for g in (-1, -4, 0, 2):
+        monkeypatch.setattr(tsc, 'gap_extend', g)
+        for T, O in [('ca', 'aa'), ('dominus', 'dns'), ('abcabc', 'abc'), ('xxxxgloriaxxxx', 'gloria')]:
+            assert tuple(tsc.perform_alignment(list(T), list(O))) == \
+                tuple(oracle.perform_alignment(list(T), list(O), None, boundary_gap=g))
+
+
+def test_empty_and_degenerate(tsc, oracle):
+    pairs = [('', ''), ('a', ''), ('', 'b'), ('abc', ''), ('', 'abc'), ('a', 'a'), ('a', 'b'),
+             ('a' * 40, 'a'), ('a', 'a' * 40), ('ab' * 70, 'ba' * 70), ('a' * 129, 'a' * 129),
+             ('a' * 33, 'b' * 1025)]
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+    out = tsc.perform_alignment_batch([(list(t), list(o)) for t, o in pairs])
+    assert out[0] == ([], [])
+    assert out[3] == (list('abc'), list('___'))
+
+
+def test_every_strip_width_and_pass_boundary(tsc, oracle):
+    """m sweeps every remainder strip width (C = 4..32) and the 1024-column pass boundary."""
+    rng = random.Random(11)
+    pairs = []
+    for m in list(range(1, 40)) + [127, 128, 129, 255, 256, 257, 383, 385, 511, 513, 640, 767, 769, 896,
+                                   1000, 1023, 1024, 1025, 1151, 1153, 2047, 2048, 2049, 2200, 3100]:
+        n = rng.choice([1, 2, 31, 32, 33, 64, 100])
+        t, o = synth.make_pair(100000 + m, n, m, 1, 12)
+        pairs.append((t, o))
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+
+
+def test_tall_pairs(tsc, oracle):
+    pairs = [synth.make_pair(300 + k, n, m, 2, 9) for k, (n, m) in
+             enumerate([(2000, 5), (1500, 40), (3000, 130), (1024, 1024), (1025, 1023), (700, 1300)])]
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+
+
+def test_random_parameters_small_alphabet(tsc, oracle):
+    """Tie-heavy inputs under random integer scoring systems, incl. positive gaps/mismatches."""
+    rng = random.Random(2024)
+    for trial in range(12):
+        alpha = rng.choice(['ab', 'abc', 'acgt'])
+        pairs = []
+        for _ in range(60):
+            n, m = rng.randint(0, 150), rng.randint(0, 150)
+            pairs.append((''.join(rng.choice(alpha) for _ in range(n)), ''.join(rng.choice(alpha) for _ in range(m))))
+        params = (rng.randint(0, 12), rng.randint(-10, 3), rng.randint(-10, 2), rng.randint(-10, 2),
+                  rng.randint(-6, 1), rng.randint(-6, 1), rng.randint(-5, 2))
+        _check_packed_vs_oracle(tsc, oracle, pairs, params)
+
+
+def test_grid_search_parameter_vectors(tsc, oracle):
+    """The reference's only batch workload: evaluate_text_alignment.py:181-188 sweeps
+    {5,8,11}x{-4,-7,-10}x{-2,-5,-7}^2x{0,-3,-5}^2; sample the grid on fixed pairs."""
+    from itertools import product
+    grid = list(product([5, 8, 11], [-4, -7, -10], [-2, -5, -7], [-2, -5, -7], [0, -3, -5], [0, -3, -5]))
+    rng = random.Random(9)
+    pairs = [synth.make_pair(500 + k, 180 + 10 * k, 230 + 7 * k, 3, 25) for k in range(3)]
+    for p in rng.sample(grid, 24):
+        _check_packed_vs_oracle(tsc, oracle, pairs, tuple(p) + (-1,))
+
+
+def test_callable_scorer_medium(tsc, oracle):
+    import scorers
+    t, o = synth.make_pair(8123, 300, 420, 3, 30)
+    for name in ('vowel_aware', 'confusable', 'asymmetric'):
+        system = [scorers.SCORERS[name], -7, -6, -3, -1]
+        got = tsc.perform_alignment(list(t), list(o), scoring_system=system, return_scores=True)
+        want = oracle.perform_alignment(list(t), list(o), system, full=True)
+        assert (got[0], got[1]) == (want[0], want[1])
+        assert tuple(got[2]) == _end(want[2]['end'])
+
+
+def test_two_char_elements_demo_shape(tsc, oracle):
+    """Elements need not be characters (textSeqCompare.py:185-186)."""
+    rng = random.Random(4)
+    T = [rng.choice(['Lo', 're', 'm ', 'ip', 'su']) for _ in range(90)]
+    O = [rng.choice(['Lo', 're', 'm ', 'ip', 'xx']) for _ in range(120)]
+    assert tuple(tsc.perform_alignment(T, O, [10, -5, -7, -7])) == tuple(oracle.perform_alignment(T, O, [10, -5, -7, -7]))
+
+
+def test_unicode_symbols(tsc, oracle):
+    T = list('dūs dominus ā ē alleluia ō') * 4
+    O = list('dns dominvs a e allelvia ō') * 4
+    assert tuple(tsc.perform_alignment(T, O)) == tuple(oracle.perform_alignment(T, O))
+
+
+def test_inputs_not_mutated_and_outputs_fresh(tsc):
+    T, O = list('gloria'), list('glorla')
+    t0, o0 = list(T), list(O)
+    a, b = tsc.perform_alignment(T, O)
+    assert T == t0 and O == o0 and len(a) == len(b)
+    a.append('x')
+    assert tsc.perform_alignment(T, O)[0] != a
+
+
+def test_verbose_prints_reference_format(tsc):
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        tra, ocr = tsc.perform_alignment(list('ab'), list('ba'), verbose=True)
+    lines = buf.getvalue().splitlines()
+    assert (tra, ocr) == (list('ab_'), list('_ba'))
+    assert lines == ['a _  ', 'b b O', '_ a  ']            # textSeqCompare.py:172-175
+
+
+def test_invalid_scoring_system_raises_before_native(tsc):
+    with pytest.raises(ValueError) as ei:
+        tsc.perform_alignment(list('a'), list('b'), scoring_system=[1, 2, 3])
+    assert str(ei.value) == 'scoring_system [1, 2, 3] invalid'
+
+
+def test_score_range_guard(tsc):
+    with pytest.raises(OverflowError):
+        tsc.perform_alignment(list('ab'), list('ab'), scoring_system=[2 ** 21, -4, -7, -7, -3, 0])
+
+
+def test_c2_sample_pages_bit_exact(tsc, oracle):
+    """BASELINE config 2 shape: 48 of the 10k seeded page pairs vs the C oracle."""
+    pairs = [synth.c2_pair(k) for k in range(48)]
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+
+
+def test_c3_lines_bit_exact(tsc, oracle):
+    pairs = [synth.c3_pair(k) for k in range(3000)]
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+
+
+def test_c4_long_insertions_bit_exact(tsc, oracle):
+    pairs = [synth.c4_pair(k) for k in range(24)]
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+
+
+def test_determinism_and_order_independence(tsc):
+    pairs = [synth.c3_pair(k) for k in range(200)] + [synth.c2_pair(k) for k in range(4)]
+    a = tsc.align_packed(*_pack(pairs), DEFAULT)
+    b = tsc.align_packed(*_pack(pairs), DEFAULT)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    rev = pairs[::-1]
+    c = tsc.align_packed(*_pack(rev), DEFAULT)
+    for k in range(len(pairs)):
+        j = len(pairs) - 1 - k
+        assert np.array_equal(a[0][a[1][k]:a[1][k] + a[2][k]], c[0][c[1][j]:c[1][j] + c[2][j]])
+
+
+def test_op_string_invariants_at_scale(tsc):
+    """Size-independent properties on a larger batch: every op string consumes exactly n
+    transcript and m OCR symbols, and the recomputed path score equals the reported corner
+    score of the state the traceback started in... (sum of per-column scores)."""
+    pairs = [synth.c2_pair(1000 + k) for k in range(64)]
+    buf, t_off, n, o_off, m = _pack(pairs)
+    ops, ops_off, ops_len, scores = tsc.align_packed(buf, t_off, n, o_off, m, DEFAULT)
+    for k in range(len(pairs)):
+        o = ops[ops_off[k]:ops_off[k] + ops_len[k]]
+        assert int((o != 2).sum()) == n[k] and int((o != 1).sum()) == m[k]
+        assert max(n[k], m[k]) <= o.size <= n[k] + m[k]

@@ -1,0 +1,243 @@
+"""ctypes binding of libtanw.so (include/tanw.h).  There is no CPU fallback: if the library
+is missing or no sm_100 device is present, every entry raises."""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtanw.so')
+
+NEG_INF = -1073741824          # TANW_NEG_INF
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+class Scoring(ctypes.Structure):
+    _fields_ = [('match', ctypes.c_int32), ('mismatch', ctypes.c_int32),
+                ('gap_open_x', ctypes.c_int32), ('gap_open_y', ctypes.c_int32),
+                ('gap_extend_x', ctypes.c_int32), ('gap_extend_y', ctypes.c_int32),
+                ('boundary_gap', ctypes.c_int32), ('subst_k', ctypes.c_int32),
+                ('subst', _i32p)]
+
+
+class DeviceInfo(ctypes.Structure):
+    _fields_ = [('name', ctypes.c_char * 128), ('cc_major', ctypes.c_int32), ('cc_minor', ctypes.c_int32),
+                ('sm_count', ctypes.c_int32), ('clock_khz', ctypes.c_int32),
+                ('total_mem_bytes', ctypes.c_int64), ('free_mem_bytes', ctypes.c_int64)]
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [('h2d_ms', ctypes.c_float), ('kernel_ms', ctypes.c_float), ('d2h_ms', ctypes.c_float),
+                ('kernel_launches', ctypes.c_int32), ('cells', ctypes.c_int64), ('ptr_bytes', ctypes.c_int64),
+                ('h2d_bytes', ctypes.c_int64), ('d2h_bytes', ctypes.c_int64)]
+
+
+# every symbol include/tanw.h declares: (restype, argtypes)
+_VOIDP = ctypes.c_void_p
+SIGNATURES = {
+    'tanw_version': (ctypes.c_int, []),
+    'tanw_device_count': (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    'tanw_device_query': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(DeviceInfo)]),
+    'tanw_last_error': (ctypes.c_char_p, [_VOIDP]),
+    'tanw_create': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_VOIDP)]),
+    'tanw_destroy': (ctypes.c_int, [_VOIDP]),
+    'tanw_set_arena_limit': (ctypes.c_int, [_VOIDP, ctypes.c_int64]),
+    'tanw_align_batch': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
+                                        ctypes.POINTER(Scoring), _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
+    'tanw_batch_prepare': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
+                                          ctypes.POINTER(Scoring)]),
+    'tanw_batch_run': (ctypes.c_int, [_VOIDP]),
+    'tanw_batch_fetch': (ctypes.c_int, [_VOIDP, _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
+    'tanw_sync': (ctypes.c_int, [_VOIDP]),
+    'tanw_last_timing': (ctypes.c_int, [_VOIDP, ctypes.POINTER(Timing)]),
+    'tanw_stream_handle': (ctypes.c_int, [_VOIDP, ctypes.POINTER(ctypes.c_uint64)]),
+    'tanw_measure_int32_peak': (ctypes.c_int, [_VOIDP, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libtanw.so (built in-tree by __graft_entry__.build()); fail loudly if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                                  '(there is no CPU fallback)' % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)      # AttributeError if the symbol is missing
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(ct)
+
+
+def device_count():
+    c = ctypes.c_int(0)
+    rc = load().tanw_device_count(ctypes.byref(c))
+    if rc:
+        raise NativeError(load().tanw_last_error(None).decode())
+    return c.value
+
+
+def device_info(device=0):
+    info = DeviceInfo()
+    rc = load().tanw_device_query(device, ctypes.byref(info))
+    if rc:
+        raise NativeError(load().tanw_last_error(None).decode())
+    return dict(name=info.name.decode(), cc=(info.cc_major, info.cc_minor), sm_count=info.sm_count,
+                clock_khz=info.clock_khz, total_mem_bytes=info.total_mem_bytes,
+                free_mem_bytes=info.free_mem_bytes)
+
+
+class Context(object):
+    """One per GPU.  Single-caller; distinct contexts may run on distinct threads (ctypes
+    releases the GIL for the duration of each native call)."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        h = _VOIDP()
+        rc = self._lib.tanw_create(int(device), ctypes.byref(h))
+        if rc:
+            raise NativeError('tanw_create(device=%d) failed: %s' % (device, self._lib.tanw_last_error(None).decode()))
+        self._h = h
+        self.device = int(device)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.tanw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            msg = self._lib.tanw_last_error(self._h).decode()
+            if rc == 2:
+                raise OverflowError(msg)
+            if rc == 1:
+                raise ValueError(msg)
+            if rc == 5:
+                raise MemoryError(msg)
+            raise NativeError('libtanw error %d: %s' % (rc, msg))
+
+    def set_arena_limit(self, nbytes):
+        self._check(self._lib.tanw_set_arena_limit(self._h, int(nbytes)))
+
+    @staticmethod
+    def _canon(symbols, t_off, n, o_off, m):
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        t_off = np.ascontiguousarray(t_off, dtype=np.int64)
+        o_off = np.ascontiguousarray(o_off, dtype=np.int64)
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        m = np.ascontiguousarray(m, dtype=np.int32)
+        if not (t_off.size == n.size == o_off.size == m.size):
+            raise ValueError('pair table arrays differ in length')
+        return symbols, t_off, n, o_off, m
+
+    @staticmethod
+    def make_scoring(match, mismatch, gox, goy, gex, gey, boundary_gap, subst=None):
+        sc = Scoring()
+        sc.match, sc.mismatch = int(match), int(mismatch)
+        sc.gap_open_x, sc.gap_open_y = int(gox), int(goy)
+        sc.gap_extend_x, sc.gap_extend_y = int(gex), int(gey)
+        sc.boundary_gap = int(boundary_gap)
+        keep = None
+        if subst is not None:
+            keep = np.ascontiguousarray(subst, dtype=np.int32)
+            if keep.ndim != 2 or keep.shape[0] != keep.shape[1]:
+                raise ValueError('substitution table must be square')
+            sc.subst_k = keep.shape[0]
+            sc.subst = _ptr(keep, _i32p)
+        return sc, keep
+
+    @staticmethod
+    def canonical_ops_layout(n, m):
+        cap = n.astype(np.int64) + m.astype(np.int64)
+        off = np.zeros(n.size, dtype=np.int64)
+        if n.size:
+            np.cumsum(cap[:-1], out=off[1:])
+        return off, int(cap.sum())
+
+    def align_batch(self, symbols, t_off, n, o_off, m, scoring, want_scores=True, out=None):
+        """One call = H2D + fill + traceback + D2H.  Returns (ops, ops_off, ops_len, scores).
+        `out` = (ops, ops_len, scores) preallocated arrays (e.g. pinned) to receive the results."""
+        symbols, t_off, n, o_off, m = self._canon(symbols, t_off, n, o_off, m)
+        sc, keep = scoring
+        P = int(n.size)
+        ops_off, total = self.canonical_ops_layout(n, m)
+        if out is not None:
+            ops, ops_len, scores = out
+            if ops.size < total or ops_len.size < P or (want_scores and scores.size < 3 * P):
+                raise ValueError('preallocated output buffers are too small')
+        else:
+            ops = np.empty(max(total, 1), dtype=np.uint8)
+            ops_len = np.zeros(max(P, 1), dtype=np.int32)
+            scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
+        rc = self._lib.tanw_align_batch(self._h, _ptr(symbols, _u8p), symbols.size, _ptr(t_off, _i64p), _ptr(n, _i32p),
+                                        _ptr(o_off, _i64p), _ptr(m, _i32p), P, ctypes.byref(sc),
+                                        _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size, _ptr(ops_len, _i32p),
+                                        _ptr(scores, _i32p) if want_scores else None)
+        self._check(rc)
+        return ops, ops_off, ops_len[:P], (scores[:P] if want_scores else None)
+
+    # ---- three-phase form (bench.py times run() alone with the inputs resident in HBM) ----
+    def prepare(self, symbols, t_off, n, o_off, m, scoring):
+        symbols, t_off, n, o_off, m = self._canon(symbols, t_off, n, o_off, m)
+        sc, keep = scoring
+        self._keep = (symbols, t_off, n, o_off, m, sc, keep)
+        self._check(self._lib.tanw_batch_prepare(self._h, _ptr(symbols, _u8p), symbols.size, _ptr(t_off, _i64p),
+                                                 _ptr(n, _i32p), _ptr(o_off, _i64p), _ptr(m, _i32p), int(n.size),
+                                                 ctypes.byref(sc)))
+
+    def run(self):
+        self._check(self._lib.tanw_batch_run(self._h))
+
+    def sync(self):
+        self._check(self._lib.tanw_sync(self._h))
+
+    def fetch(self, want_scores=True):
+        _, _, n, _, m, _, _ = self._keep
+        P = int(n.size)
+        ops_off, total = self.canonical_ops_layout(n, m)
+        ops = np.empty(max(total, 1), dtype=np.uint8)
+        ops_len = np.zeros(max(P, 1), dtype=np.int32)
+        scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
+        self._check(self._lib.tanw_batch_fetch(self._h, _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size,
+                                               _ptr(ops_len, _i32p), _ptr(scores, _i32p) if want_scores else None))
+        return ops, ops_off, ops_len[:P], (scores[:P] if want_scores else None)
+
+    def timing(self):
+        t = Timing()
+        self._check(self._lib.tanw_last_timing(self._h, ctypes.byref(t)))
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def stream_handle(self):
+        v = ctypes.c_uint64(0)
+        self._check(self._lib.tanw_stream_handle(self._h, ctypes.byref(v)))
+        return v.value
+
+    def measure_int32_peak(self, which=0):
+        v = ctypes.c_double(0.0)
+        self._check(self._lib.tanw_measure_int32_peak(self._h, int(which), ctypes.byref(v)))
+        return v.value

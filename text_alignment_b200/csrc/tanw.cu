@@ -1,0 +1,535 @@
+// tanw.cu -- host side of libtanw.so: the C ABI declared in include/tanw.h.
+//
+// Replaces the per-page call textSeqCompare.perform_alignment (textSeqCompare.py:13-177,
+// call site alignToOCR.py:273-274) by a batched device implementation.  No CPU fallback:
+// every entry either runs on an sm_100 device or returns an error.
+#include "tanw.h"
+#include "tanw_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace tanw;
+
+namespace {
+
+thread_local std::string g_last_error;   // for failures that have no context yet
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct tanw_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr,
+                ev_d2h0 = nullptr, ev_d2h1 = nullptr;
+    std::string err;
+    int64_t arena_limit = 0;
+
+    DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst;
+    std::vector<PairDesc> h_pairs;
+    std::vector<int> h_order;
+    std::vector<int64_t> h_ops_off;       // canonical device layout: prefix sums of n+m
+    std::vector<uint8_t> h_stage;         // used when the caller's op layout is not canonical
+
+    // state of the prepared batch
+    bool prepared = false, ran = false;
+    int64_t n_pairs = 0, ops_total = 0;
+    KParams kp;
+    bool use_subst = false;
+    BatchArgs args;
+    int grid = 0;
+    int occ_plain = 0, occ_subst = 0;
+    tanw_timing timing;
+};
+
+namespace {
+
+int fail(tanw_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_last_error = buf;
+    return code;
+}
+
+#define TANW_CUDA(ctx, call)                                                              \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(ctx, TANW_E_CUDA, "%s failed: %s (%s:%d)", #call,                 \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+    } while (0)
+
+bool device_is_blackwell(int device, cudaDeviceProp *prop_out)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return false;
+    if (prop_out) *prop_out = prop;
+    return prop.major == 10;
+}
+
+// int32 fixed point: every finite intermediate must stay far away from kNeg = -2^30.
+// |value| <= (n+m+2) * max|param| ; carried << 6 and offset by up to ex*n once more.
+bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
+{
+    int64_t pmax = 1;
+    auto upd = [&](int64_t v) { pmax = std::max<int64_t>(pmax, v < 0 ? -v : v); };
+    upd(s->match); upd(s->mismatch); upd(s->boundary_gap);
+    upd((int64_t)s->gap_open_x + s->gap_extend_x); upd(s->gap_extend_x);
+    upd((int64_t)s->gap_open_y + s->gap_extend_y); upd(s->gap_extend_y);
+    if (s->subst)
+        for (int64_t i = 0; i < (int64_t)s->subst_k * s->subst_k; ++i) upd(s->subst[i]);
+    return (max_n_plus_m + 2) * pmax < (int64_t(1) << 22);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tanw_version(void) { return 100; }
+
+const char *tanw_last_error(const tanw_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+int tanw_device_count(int *count)
+{
+    if (!count) return fail(nullptr, TANW_E_INVALID, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(nullptr, TANW_E_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = c;
+    return TANW_OK;
+}
+
+int tanw_device_query(int device, tanw_device_info *out)
+{
+    if (!out) return fail(nullptr, TANW_E_INVALID, "out is NULL");
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess)
+        return fail(nullptr, TANW_E_NODEVICE, "device %d: %s", device, cudaGetErrorString(e));
+    memset(out, 0, sizeof *out);
+    snprintf(out->name, sizeof out->name, "%s", prop.name);
+    out->cc_major = prop.major;
+    out->cc_minor = prop.minor;
+    out->sm_count = prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    out->clock_khz = khz;
+    out->total_mem_bytes = (int64_t)prop.totalGlobalMem;
+    size_t fr = 0, tot = 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cudaSetDevice(device) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess)
+        out->free_mem_bytes = (int64_t)fr;
+    cudaSetDevice(cur);
+    return TANW_OK;
+}
+
+int tanw_create(int device, tanw_ctx **out)
+{
+    if (!out) return fail(nullptr, TANW_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(nullptr, TANW_E_NODEVICE, "no CUDA device visible (libtanw has no CPU fallback)");
+    if (device < 0 || device >= count)
+        return fail(nullptr, TANW_E_NODEVICE, "device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    if (!device_is_blackwell(device, &prop))
+        return fail(nullptr, TANW_E_NODEVICE,
+                    "device %d (%s, sm_%d%d) is not an sm_100 part; libtanw is built for sm_100a only",
+                    device, prop.name, prop.major, prop.minor);
+    tanw_ctx *ctx = new (std::nothrow) tanw_ctx();
+    if (!ctx) return fail(nullptr, TANW_E_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaEvent_t *evs[] = { &ctx->ev_h2d0, &ctx->ev_h2d1, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_d2h0, &ctx->ev_d2h1 };
+    for (auto ev : evs)
+        if (e == cudaSuccess) e = cudaEventCreate(ev);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_plain, align_pairs_kernel<false>,
+                                                          kWarpsPerBlock * 32, 0);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_subst, align_pairs_kernel<true>,
+                                                          kWarpsPerBlock * 32, 0);
+    if (e != cudaSuccess) {
+        int rc = fail(nullptr, TANW_E_CUDA, "context setup on device %d: %s", device, cudaGetErrorString(e));
+        tanw_destroy(ctx);
+        return rc;
+    }
+    if (ctx->occ_plain < 1) ctx->occ_plain = 1;
+    if (ctx->occ_subst < 1) ctx->occ_subst = 1;
+    *out = ctx;
+    return TANW_OK;
+}
+
+int tanw_destroy(tanw_ctx *ctx)
+{
+    if (!ctx) return TANW_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_pairs, &ctx->d_order, &ctx->d_counter, &ctx->d_arena,
+                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst };
+    for (auto b : bufs) b->release();
+    cudaEvent_t evs[] = { ctx->ev_h2d0, ctx->ev_h2d1, ctx->ev_k0, ctx->ev_k1, ctx->ev_d2h0, ctx->ev_d2h1 };
+    for (auto ev : evs)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TANW_OK;
+}
+
+int tanw_set_arena_limit(tanw_ctx *ctx, int64_t bytes)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    if (bytes < 0) return fail(ctx, TANW_E_INVALID, "arena limit must be >= 0");
+    ctx->arena_limit = bytes;
+    return TANW_OK;
+}
+
+int tanw_stream_handle(tanw_ctx *ctx, uint64_t *out)
+{
+    if (!ctx || !out) return fail(ctx, TANW_E_INVALID, "NULL argument");
+    *out = (uint64_t)(uintptr_t)ctx->stream;
+    return TANW_OK;
+}
+
+int tanw_sync(tanw_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+    TANW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TANW_OK;
+}
+
+int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_len,
+                       const int64_t *t_off, const int32_t *n, const int64_t *o_off,
+                       const int32_t *m, int64_t n_pairs, const tanw_scoring *sc)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    ctx->prepared = false;
+    ctx->ran = false;
+    if (n_pairs < 0 || symbols_len < 0) return fail(ctx, TANW_E_INVALID, "negative size");
+    if (n_pairs > 0 && (!t_off || !n || !o_off || !m)) return fail(ctx, TANW_E_INVALID, "NULL pair table");
+    if (symbols_len > 0 && !symbols) return fail(ctx, TANW_E_INVALID, "symbols is NULL");
+    if (!sc) return fail(ctx, TANW_E_INVALID, "scoring is NULL");
+    if (n_pairs > 0x7fffffff) return fail(ctx, TANW_E_INVALID, "more than 2^31-1 pairs in one batch");
+    if (sc->subst && (sc->subst_k < 1 || sc->subst_k > 256))
+        return fail(ctx, TANW_E_INVALID, "subst_k must be in 1..256");
+
+    // ---- pair table, canonical op layout, size statistics --------------------------------
+    ctx->h_pairs.resize((size_t)n_pairs);
+    ctx->h_ops_off.resize((size_t)n_pairs);
+    int64_t ops_total = 0, cells = 0, ptr_total = 0, max_nm = 0, max_slot = 0;
+    int max_n = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int64_t np = n[p], mp = m[p];
+        if (np < 0 || mp < 0) return fail(ctx, TANW_E_INVALID, "pair %lld: negative length", (long long)p);
+        if (t_off[p] < 0 || o_off[p] < 0 || t_off[p] + np > symbols_len || o_off[p] + mp > symbols_len)
+            return fail(ctx, TANW_E_INVALID, "pair %lld: offsets outside the symbol buffer", (long long)p);
+        PairDesc &pd = ctx->h_pairs[(size_t)p];
+        pd.t_off = t_off[p]; pd.o_off = o_off[p]; pd.n = (int)np; pd.m = (int)mp;
+        pd.ops_off = ops_total;
+        ctx->h_ops_off[(size_t)p] = ops_total;
+        ops_total += np + mp;
+        cells += np * mp;
+        const int64_t pb = ptr_bytes((int)np, (int)mp);
+        ptr_total += np * mp;
+        max_slot = std::max(max_slot, pb);
+        max_nm = std::max(max_nm, np + mp);
+        max_n = std::max(max_n, (int)np);
+    }
+    if (!scoring_in_range(sc, max_nm))
+        return fail(ctx, TANW_E_RANGE,
+                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^22");
+    if (sc->subst) {
+        int maxsym = 0;
+        for (int64_t i = 0; i < symbols_len; ++i) maxsym = std::max<int>(maxsym, symbols[i]);
+        if (symbols_len > 0 && maxsym >= sc->subst_k)
+            return fail(ctx, TANW_E_INVALID, "symbol code %d >= subst_k %d", maxsym, sc->subst_k);
+    }
+
+    // ---- work order: largest pairs first (greedy longest-processing-time) ------------------
+    ctx->h_order.resize((size_t)n_pairs);
+    std::iota(ctx->h_order.begin(), ctx->h_order.end(), 0);
+    {
+        const std::vector<PairDesc> &hp = ctx->h_pairs;
+        std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&hp](int a, int b) {
+            return (int64_t)hp[(size_t)a].n * hp[(size_t)a].m > (int64_t)hp[(size_t)b].n * hp[(size_t)b].m;
+        });
+    }
+
+    // ---- kernel parameters ------------------------------------------------------------------
+    KParams &kp = ctx->kp;
+    memset(&kp, 0, sizeof kp);
+    kp.maT = (sc->match << kShift) | kTagM;
+    kp.miT = (sc->mismatch << kShift) | kTagM;
+    kp.ox = (sc->gap_open_x + sc->gap_extend_x) * (1 << kShift);
+    kp.ex = sc->gap_extend_x * (1 << kShift);
+    kp.oy = (sc->gap_open_y + sc->gap_extend_y) * (1 << kShift);
+    kp.ey = sc->gap_extend_y * (1 << kShift);
+    kp.bg = sc->boundary_gap * (1 << kShift);
+    for (int k = 0; k < kMaxC; ++k) { kp.cy[k] = kp.oy - kp.ey * k; kp.ye[k] = kp.ey * k; }
+    ctx->use_subst = sc->subst != nullptr;
+
+    TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // ---- launch geometry and scratch ----------------------------------------------------------
+    const int occ = ctx->use_subst ? ctx->occ_subst : ctx->occ_plain;
+    int grid = ctx->sm_count * occ;
+    const int64_t need_blocks = (n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (need_blocks < grid) grid = (int)std::max<int64_t>(need_blocks, 1);
+    const int64_t slot_bytes = (max_slot + 255) / 256 * 256;
+    int64_t limit = ctx->arena_limit;
+    if (limit == 0) {
+        size_t fr = 0, tot = 0;
+        TANW_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+        limit = (int64_t)(tot / 10 * 4);
+    }
+    if (slot_bytes > 0) {
+        int64_t max_blocks = limit / (slot_bytes * kWarpsPerBlock);
+        if (max_blocks < 1)
+            return fail(ctx, TANW_E_NOMEM,
+                        "a pair needs %lld bytes of traceback pointers per warp; arena limit is %lld "
+                        "(use the striped long-pair path)", (long long)slot_bytes, (long long)limit);
+        if (max_blocks < grid) grid = (int)max_blocks;
+    }
+    ctx->grid = grid;
+    const int64_t slots = (int64_t)grid * kWarpsPerBlock;
+    const int bnd_rows = max_n + 2;
+
+    // ---- device buffers and uploads -------------------------------------------------------
+    if (ctx->d_sym.reserve((size_t)symbols_len + 16) != cudaSuccess ||
+        ctx->d_pairs.reserve(sizeof(PairDesc) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
+        ctx->d_order.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
+        ctx->d_counter.reserve(256) != cudaSuccess ||
+        ctx->d_arena.reserve((size_t)std::max<int64_t>(slots * slot_bytes, 256)) != cudaSuccess ||
+        ctx->d_bnd.reserve(sizeof(int2) * (size_t)(slots * bnd_rows)) != cudaSuccess ||
+        ctx->d_ops.reserve((size_t)ops_total + 64) != cudaSuccess ||
+        ctx->d_len.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
+        ctx->d_scores.reserve(sizeof(int) * 3 * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, TANW_E_NOMEM, "device allocation failed (arena %lld bytes)", (long long)(slots * slot_bytes));
+    }
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d0, ctx->stream));
+    int64_t h2d = 0;
+    if (symbols_len > 0) {
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sym.p, symbols, (size_t)symbols_len, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += symbols_len;
+    }
+    if (n_pairs > 0) {
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairDesc) * (size_t)n_pairs,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * (size_t)n_pairs,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        h2d += (int64_t)(sizeof(PairDesc) + sizeof(int)) * n_pairs;
+    }
+    if (ctx->use_subst) {
+        const size_t kk = (size_t)sc->subst_k * (size_t)sc->subst_k;
+        std::vector<int> tab(kk);
+        for (size_t i = 0; i < kk; ++i) tab[i] = (sc->subst[i] * (1 << kShift)) | kTagM;
+        if (ctx->d_subst.reserve(sizeof(int) * kk) != cudaSuccess)
+            return fail(ctx, TANW_E_NOMEM, "device allocation failed (substitution table)");
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_subst.p, tab.data(), sizeof(int) * kk, cudaMemcpyHostToDevice, ctx->stream));
+        TANW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // tab is a local
+        kp.subst = (const int *)ctx->d_subst.p;
+        kp.subst_k = sc->subst_k;
+        h2d += (int64_t)(sizeof(int) * kk);
+    }
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d1, ctx->stream));
+
+    BatchArgs &a = ctx->args;
+    a.sym = (const uint8_t *)ctx->d_sym.p;
+    a.pairs = (const PairDesc *)ctx->d_pairs.p;
+    a.order = (const int *)ctx->d_order.p;
+    a.counter = (unsigned *)ctx->d_counter.p;
+    a.n_pairs = (int)n_pairs;
+    a.ptr_arena = (uint8_t *)ctx->d_arena.p;
+    a.slot_bytes = slot_bytes;
+    a.bnd_arena = (int2 *)ctx->d_bnd.p;
+    a.bnd_rows = bnd_rows;
+    a.ops = (uint8_t *)ctx->d_ops.p;
+    a.ops_len = (int *)ctx->d_len.p;
+    a.scores = (int *)ctx->d_scores.p;
+
+    ctx->n_pairs = n_pairs;
+    ctx->ops_total = ops_total;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->timing.cells = cells;
+    ctx->timing.ptr_bytes = ptr_total;
+    ctx->timing.h2d_bytes = h2d;
+    ctx->prepared = true;
+    return TANW_OK;
+}
+
+int tanw_batch_run(tanw_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    if (!ctx->prepared) return fail(ctx, TANW_E_STATE, "tanw_batch_run before tanw_batch_prepare");
+    TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+    int launches = 0;
+    if (ctx->n_pairs > 0) {
+        TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned), ctx->stream));
+        if (ctx->use_subst)
+            align_pairs_kernel<true><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
+        else
+            align_pairs_kernel<false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
+        TANW_CUDA(ctx, cudaGetLastError());
+        launches = 1;
+    }
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+    ctx->timing.kernel_launches = launches;
+    ctx->ran = true;
+    return TANW_OK;
+}
+
+int tanw_batch_fetch(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
+                     int32_t *ops_len, int32_t *scores)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    if (!ctx->ran) return fail(ctx, TANW_E_STATE, "tanw_batch_fetch before tanw_batch_run");
+    const int64_t P = ctx->n_pairs;
+    if (P > 0 && (!ops_off || !ops_len)) return fail(ctx, TANW_E_INVALID, "NULL output table");
+    if (ctx->ops_total > 0 && !ops) return fail(ctx, TANW_E_INVALID, "ops is NULL");
+    bool canonical = true;
+    for (int64_t p = 0; p < P; ++p) {
+        const int64_t cap = (int64_t)ctx->h_pairs[(size_t)p].n + ctx->h_pairs[(size_t)p].m;
+        if (ops_off[p] < 0 || ops_off[p] + cap > ops_capacity)
+            return fail(ctx, TANW_E_INVALID, "pair %lld: op buffer too small (needs n+m = %lld bytes at offset %lld)",
+                        (long long)p, (long long)cap, (long long)ops_off[p]);
+        if (ops_off[p] != ctx->h_ops_off[(size_t)p]) canonical = false;
+    }
+    TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h0, ctx->stream));
+    int64_t d2h = 0;
+    uint8_t *dst = ops;
+    if (!canonical) {
+        ctx->h_stage.resize((size_t)ctx->ops_total);
+        dst = ctx->h_stage.data();
+    }
+    if (ctx->ops_total > 0) {
+        TANW_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_ops.p, (size_t)ctx->ops_total, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += ctx->ops_total;
+    }
+    if (P > 0) {
+        TANW_CUDA(ctx, cudaMemcpyAsync(ops_len, ctx->d_len.p, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += (int64_t)sizeof(int) * P;
+        if (scores) {
+            TANW_CUDA(ctx, cudaMemcpyAsync(scores, ctx->d_scores.p, sizeof(int) * 3 * (size_t)P,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+            d2h += (int64_t)sizeof(int) * 3 * P;
+        }
+    }
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h1, ctx->stream));
+    TANW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!canonical)
+        for (int64_t p = 0; p < P; ++p)
+            memcpy(ops + ops_off[p], ctx->h_stage.data() + ctx->h_ops_off[(size_t)p], (size_t)ops_len[p]);
+    ctx->timing.d2h_bytes = d2h;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_h2d0, ctx->ev_h2d1) == cudaSuccess) ctx->timing.h2d_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->timing.kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev_d2h0, ctx->ev_d2h1) == cudaSuccess) ctx->timing.d2h_ms = ms;
+    cudaGetLastError();
+    return TANW_OK;
+}
+
+int tanw_align_batch(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_len,
+                     const int64_t *t_off, const int32_t *n, const int64_t *o_off, const int32_t *m,
+                     int64_t n_pairs, const tanw_scoring *scoring, uint8_t *ops, const int64_t *ops_off,
+                     int64_t ops_capacity, int32_t *ops_len, int32_t *scores)
+{
+    int rc = tanw_batch_prepare(ctx, symbols, symbols_len, t_off, n, o_off, m, n_pairs, scoring);
+    if (rc) return rc;
+    rc = tanw_batch_run(ctx);
+    if (rc) return rc;
+    return tanw_batch_fetch(ctx, ops, ops_off, ops_capacity, ops_len, scores);
+}
+
+int tanw_last_timing(tanw_ctx *ctx, tanw_timing *out)
+{
+    if (!ctx || !out) return fail(ctx, TANW_E_INVALID, "NULL argument");
+    if (ctx->ran) {
+        // valid once the stream has drained past the kernel (after fetch or tanw_sync)
+        float ms = 0.f;
+        if (cudaEventQuery(ctx->ev_k1) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess)
+            ctx->timing.kernel_ms = ms;
+        if (cudaEventQuery(ctx->ev_h2d1) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ctx->ev_h2d0, ctx->ev_h2d1) == cudaSuccess)
+            ctx->timing.h2d_ms = ms;
+        cudaGetLastError();
+    }
+    *out = ctx->timing;
+    return TANW_OK;
+}
+
+int tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s)
+{
+    if (!ctx || !lane_ops_per_s) return fail(ctx, TANW_E_INVALID, "NULL argument");
+    if (which < 0 || which > 2) return fail(ctx, TANW_E_INVALID, "which must be 0, 1 or 2");
+    TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->d_counter.reserve(256) != cudaSuccess) return fail(ctx, TANW_E_NOMEM, "device allocation failed");
+    const int iters = 1 << 14, blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    TANW_CUDA(ctx, cudaEventCreate(&e0));
+    TANW_CUDA(ctx, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        TANW_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        int *sink = (int *)ctx->d_counter.p + 8;
+        if (which == 0)      int32_peak_kernel<0><<<blocks, threads, 0, ctx->stream>>>(iters, 3, 5, sink);
+        else if (which == 1) int32_peak_kernel<1><<<blocks, threads, 0, ctx->stream>>>(iters, 3, 5, sink);
+        else                 int32_peak_kernel<2><<<blocks, threads, 0, ctx->stream>>>(iters, 3, 5, sink);
+        TANW_CUDA(ctx, cudaGetLastError());
+        TANW_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        TANW_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        TANW_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)blocks * threads * (double)iters * 16.0 * (which == 2 ? 2.0 : 1.0);
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *lane_ops_per_s = best;
+    return TANW_OK;
+}
+
+}  // extern "C"
