@@ -304,8 +304,9 @@ def main():
     out = (t_ops.numpy(), t_len.numpy(), t_sc.numpy())
 
     ext = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device('cuda', local_rank))
-    int32_peak = max(ctx.measure_int32_peak(0), ctx.measure_int32_peak(1))
-    int32_fused = ctx.measure_int32_peak(2)
+    # measured issue rates (warp-lane instructions/s): IADD3, VIMNMX, fused VIADDMNMX
+    rate_add, rate_max, rate_fused = (ctx.measure_int32_peak(w) for w in (0, 1, 2))
+    int32_peak = max(rate_add, rate_max)
 
     def barrier():
         torch.cuda.synchronize()
@@ -382,9 +383,13 @@ def main():
             gpu_launches=launches,
             roofline=dict(bound='alu', achieved=ach_ops / 1e12, peak=int32_peak / 1e12, unit='Tlane-op/s',
                           frac=ach_ops / int32_peak, traffic=None,
-                          note='%d algorithmic int32 ops/cell (SURVEY 8(d)) / measured IADD-VIMNMX issue peak; '
-                               'nominal alu-pipe peak %.1f' % (OPS_PER_CELL, NOMINAL_INT32_PEAK / 1e12),
-                          fused_peak=int32_fused / 1e12,
+                          note='achieved = %d algorithmic int32 ops/cell (SURVEY 8(d)) x cells / launch time; '
+                               'peak = measured dependency-free add.s32 / max.s32 issue rate on all SMs '
+                               '(tanw_measure_int32_peak); nominal alu-pipe figure of SURVEY 8(d) is %.1f'
+                               % (OPS_PER_CELL, NOMINAL_INT32_PEAK / 1e12),
+                          measured_rates=dict(iadd3=rate_add / 1e12, vimnmx=rate_max / 1e12,
+                                              viaddmnmx=rate_fused / 1e12),
+                          frac_of_nominal_alu_pipe=ach_ops / NOMINAL_INT32_PEAK,
                           hbm=dict(bound='hbm', achieved=ach_gbs, peak=hbm_peak, unit='GB/s',
                                    frac=ach_gbs / hbm_peak, peak_source=hbm_src)),
             clocks=clocks)

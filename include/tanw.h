@@ -132,10 +132,10 @@ int  tanw_last_timing(tanw_ctx *ctx, tanw_timing *out);
  * device memory of its own (e.g. torch) can order work against it. */
 int  tanw_stream_handle(tanw_ctx *ctx, uint64_t *out);
 
-/* ---- measurement helper: dependency-free int32 add/max throughput of this device ------------
- * Measures the roofline denominator SURVEY.md 8(d) asks the builder to measure:
- * lane-ops per second of IADD3 / VIMNMX issued from every SM.  `which`: 0 = add, 1 = max,
- * 2 = fused add+max (VIADDMNMX counted as 2 ops). */
+/* ---- measurement helper: dependency-free int32 issue rate of this device -----------------------
+ * Measures the roofline denominator SURVEY.md 8(d) asks the builder to measure: warp-lane
+ * INSTRUCTIONS per second issued from every SM, 16 independent chains per thread.
+ * `which`: 0 = IADD3 (add.s32), 1 = VIMNMX (max.s32/min.s32), 2 = VIADDMNMX (fused add+max). */
 int  tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s);
 
 #ifdef __cplusplus

@@ -393,23 +393,40 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
 }
 
 // ---- int32 issue-rate micro-benchmark (roofline denominator) -----------------
+// 16 independent chains per thread, operands loaded from memory so ptxas cannot fold them.
+//   WHICH 0: two add.s32 per chain-iteration, which ptxas merges into ONE 3-input IADD3
+//   WHICH 1: max.s32 + min.s32  -> two VIMNMX
+//   WHICH 2: fused add+max, add+min -> two VIADDMNMX
+// The host counts INSTRUCTIONS (1, 2, 2 per chain-iteration); see tools/int32_pipes.cu for
+// the full table of pipes.
 template <int WHICH>
-__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, int c, int d, int *sink)
+__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, const int *__restrict__ src, int *sink)
 {
-    int x[16];
+    int x[16], a[16], b[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) x[j] = threadIdx.x + j * c;
+    for (int j = 0; j < 16; ++j) {
+        x[j] = src[threadIdx.x + j * 7];
+        a[j] = src[threadIdx.x + j * 5 + 1];
+        b[j] = src[threadIdx.x + j * 3 + 2];
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            if (WHICH == 0)      asm volatile("add.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(c));
-            else if (WHICH == 1) asm volatile("max.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(d + j));
-            else                 x[j] = __viaddmax_s32(x[j], c, d + j);
+            if (WHICH == 0) {
+                asm volatile("add.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(a[j]));
+                asm volatile("add.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(b[j]));
+            } else if (WHICH == 1) {
+                asm volatile("max.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(a[j]));
+                asm volatile("min.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(b[j]));
+            } else {
+                x[j] = __viaddmax_s32(x[j], a[j], b[j]);
+                x[j] = __viaddmin_s32(x[j], b[j], a[j]);
+            }
         }
     }
     int acc = 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc ^= x[j];
+    for (int j = 0; j < 16; ++j) acc ^= x[j] ^ a[j] ^ b[j];
     if (acc == 0x7fffffff) sink[0] = acc;
 }
 
