@@ -91,62 +91,69 @@ WORKLOADS = {
 # ---- clocks ----------------------------------------------------------------------------------
 
 class ClockSampler(object):
-    """nvidia-smi sampling DURING the timed region (profiling recipe's clocks line)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle-reason sampling DURING the timed region (profiling recipe's clocks
+    line), through NVML in a background thread (an nvidia-smi -lms child polling the driver
+    was measured to stall synchronous CUDA calls of the timed process by several ms)."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.05):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.period = period_s
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.err = None
+        self.th = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, power, reasons = [], [], [], set()
-        for ts, line in self.lines:
-            f = [x.strip() for x in line.split(',')]
-            if len(f) < 9:
-                continue
-            inside = t0 <= ts <= t1 + 0.1
-            try:
-                if inside:
-                    sm.append(float(f[1])); power.append(float(f[3]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            if inside:
-                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                    if val.lower().startswith('active'):
-                        reasons.add(name)
-        if not sm:      # region shorter than the sampling period: use every sample we have
-            for ts, line in self.lines:
-                f = [x.strip() for x in line.split(',')]
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            idx = self.gpu
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
                 try:
-                    sm.append(float(f[1]))
+                    idx = int(vis.split(',')[self.gpu])
                 except (ValueError, IndexError):
                     pass
-        return dict(sm_mhz=float(np.median(sm)) if sm else None,
-                    sm_max_mhz=max(smax) if smax else None,
-                    power_w_max=max(power) if power else None,
-                    samples=len(sm), reasons=sorted(reasons))
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                       # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:                    # noqa: BLE001
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), clk, reasons, pw))
+            except Exception as e:                   # noqa: BLE001
+                self.err = repr(e)
+            self.stop_flag.wait(self.period)
+
+    def stop(self, t0, t1):
+        self.stop_flag.set()
+        if self.th is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvml unavailable: %s' % self.err])
+        self.th.join(timeout=1.0)
+        nv = self.nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in inside))
+        return dict(sm_mhz=float(np.median([s[1] for s in inside])) if inside else None,
+                    sm_max_mhz=float(self.smax), power_w_max=max(s[3] for s in inside) if inside else None,
+                    samples=len(inside), reasons=reasons, how='NVML, %d ms period' % int(self.period * 1e3))
 
 
 # ---- CPU baseline (oracle: the only place bench.py may execute oracle/) -------------------------
@@ -337,12 +344,15 @@ def main():
     launches = args.steps * ctx.timing()['kernel_launches']
 
     # ---- leg 2: end to end through the C ABI with host buffers ------------------------------------
-    for _ in range(2):
+    for _ in range(max(args.warmup, 5)):      # first calls on fresh pinned buffers are erratic (20-100 ms)
         ctx.align_batch(p_buf[1], t_off, n, o_off, m, scoring, out=out)
     barrier()
     x0 = time.perf_counter()
+    step_ms = []
     for _ in range(args.steps):
+        s0 = time.perf_counter()
         ctx.align_batch(p_buf[1], t_off, n, o_off, m, scoring, out=out)
+        step_ms.append(round((time.perf_counter() - s0) * 1e3, 3))
     barrier()
     x1 = time.perf_counter()
     tm = ctx.timing()
@@ -378,7 +388,7 @@ def main():
             wall_ms_per_step=wall_s * 1e3 / args.steps,
             e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=int(tm['h2d_bytes']),
                      d2h_bytes_per_step=int(tm['d2h_bytes']), pages_per_s=tot_pairs * args.steps / (e2e_ms * 1e-3),
-                     ms_per_step=e2e_ms / args.steps,
+                     ms_per_step=e2e_ms / args.steps, rank0_step_ms=step_ms,
                      breakdown_ms=dict(h2d=tm['h2d_ms'], kernel=tm['kernel_ms'], d2h=tm['d2h_ms'])),
             gpu_launches=launches,
             roofline=dict(bound='alu', achieved=ach_ops / 1e12, peak=int32_peak / 1e12, unit='Tlane-op/s',

@@ -215,7 +215,7 @@ def test_invalid_scoring_system_raises_before_native(tsc):
 
 def test_score_range_guard(tsc):
     with pytest.raises(OverflowError):
-        tsc.perform_alignment(list('ab'), list('ab'), scoring_system=[2 ** 21, -4, -7, -7, -3, 0])
+        tsc.perform_alignment(list('ab'), list('ab'), scoring_system=[2 ** 24, -4, -7, -7, -3, 0])
 
 
 def test_c2_sample_pages_bit_exact(tsc, oracle):

@@ -7,7 +7,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtanw.so')
+LIB_PATH = os.environ.get('TANW_LIB') or os.path.join(_HERE, 'libtanw.so')   # TANW_LIB: kernel-variant experiments
 
 NEG_INF = -1073741824          # TANW_NEG_INF
 

@@ -96,7 +96,7 @@ bool device_is_blackwell(int device, cudaDeviceProp *prop_out)
 }
 
 // int32 fixed point: every finite intermediate must stay far away from kNeg = -2^30.
-// |value| <= (n+m+2) * max|param| ; carried << 6 and offset by up to ex*n once more.
+// |value| <= (n+m+2) * max|param| ; carried << 2 and offset by up to ex*n once more.
 bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
 {
     int64_t pmax = 1;
@@ -106,7 +106,7 @@ bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
     upd((int64_t)s->gap_open_y + s->gap_extend_y); upd(s->gap_extend_y);
     if (s->subst)
         for (int64_t i = 0; i < (int64_t)s->subst_k * s->subst_k; ++i) upd(s->subst[i]);
-    return (max_n_plus_m + 2) * pmax < (int64_t(1) << 22);
+    return (max_n_plus_m + 2) * pmax < (int64_t(1) << 25);
 }
 
 }  // namespace
@@ -183,10 +183,10 @@ int tanw_create(int device, tanw_ctx **out)
     for (auto ev : evs)
         if (e == cudaSuccess) e = cudaEventCreate(ev);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_plain, align_pairs_kernel<false>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_plain, align_pairs_kernel<false, false>,
                                                           kWarpsPerBlock * 32, 0);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_subst, align_pairs_kernel<true>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_subst, align_pairs_kernel<true, false>,
                                                           kWarpsPerBlock * 32, 0);
     if (e != cudaSuccess) {
         int rc = fail(nullptr, TANW_E_CUDA, "context setup on device %d: %s", device, cudaGetErrorString(e));
@@ -277,7 +277,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     }
     if (!scoring_in_range(sc, max_nm))
         return fail(ctx, TANW_E_RANGE,
-                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^22");
+                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^25");
     if (sc->subst) {
         int maxsym = 0;
         for (int64_t i = 0; i < symbols_len; ++i) maxsym = std::max<int>(maxsym, symbols[i]);
@@ -305,7 +305,6 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     kp.oy = (sc->gap_open_y + sc->gap_extend_y) * (1 << kShift);
     kp.ey = sc->gap_extend_y * (1 << kShift);
     kp.bg = sc->boundary_gap * (1 << kShift);
-    for (int k = 0; k < kMaxC; ++k) { kp.cy[k] = kp.oy - kp.ey * k; kp.ye[k] = kp.ey * k; }
     ctx->use_subst = sc->subst != nullptr;
 
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -332,7 +331,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     }
     ctx->grid = grid;
     const int64_t slots = (int64_t)grid * kWarpsPerBlock;
-    const int bnd_rows = max_n + 2;
+    const int bnd_rows = max_n + 4;      // bnd[1..n] plus the prefetch overrun
 
     // ---- device buffers and uploads -------------------------------------------------------
     if (ctx->d_sym.reserve((size_t)symbols_len + 16) != cudaSuccess ||
@@ -407,10 +406,14 @@ int tanw_batch_run(tanw_ctx *ctx)
     int launches = 0;
     if (ctx->n_pairs > 0) {
         TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned), ctx->stream));
+        // three instantiations: tabulated scorer; equality scorer; equality scorer with
+        // gap_extend_y == 0 (the reference's default_sys), which drops one add per cell
         if (ctx->use_subst)
-            align_pairs_kernel<true><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
+            align_pairs_kernel<true, false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
+        else if (ctx->kp.ey == 0)
+            align_pairs_kernel<false, true><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
         else
-            align_pairs_kernel<false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
+            align_pairs_kernel<false, false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
         TANW_CUDA(ctx, cudaGetLastError());
         launches = 1;
     }

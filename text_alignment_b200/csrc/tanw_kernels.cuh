@@ -12,42 +12,47 @@
 //   * all H/E/F state (here M/X/Y) lives in registers: per column W = max(M,Y), X and
 //     D = max(M,X,Y) of the row above, per step the running Q = max(M,X) and Y of the column
 //     to the left;
-//   * scores are carried in int32 fixed point, value*64, and the low six bits hold the origin
-//     tag of a value (M = 0b101010, X = 0b010101, Y = 0).  A plain integer max over tagged
-//     candidates therefore returns the maximum AND, on equal values, the candidate that comes
-//     first in the reference's list order (M, X, Y) -- list.index(max(list)),
+//   * scores are carried in int32 fixed point, value*4, and the low two bits hold the origin
+//     tag of a value (M = 2, X = 1, Y = 0).  A plain integer max over tagged candidates
+//     therefore returns the maximum AND, on equal values, the candidate that comes first in
+//     the reference's list order (M, X, Y) -- list.index(max(list)),
 //     textSeqCompare.py:72,:80,:88 -- without any compare/select for the argmax;
-//   * the three 2-bit traceback pointers of a cell are cut out of the three raw max results
-//     with two bit-selects and written as one byte per cell, step-major so that every warp
-//     store is one contiguous 32*C byte segment;
-//   * the gap-extension additions are folded into per-row / per-column offsets
-//     (X^ = X - ex*i, Y^ = Y - ey*k) so each recurrence is a single VIADDMNMX;
-//   * the traceback runs in the same kernel right after the pair's fill, on the GPU, and
-//     emits the op string.
+//   * B200 issues integer min/max/logic on the "alu" pipe and IMAD on the "fma" pipe, 64
+//     lanes/clk/SM each (profiles/r1_int32_pipes.txt).  The recurrences need the alu pipe
+//     (VIADDMNMX, LOP3), so everything else is phrased as IMAD work: the three 2-bit
+//     traceback pointers of a cell are (raw max result) - (its cleaned value), and four
+//     cells' pointers are accumulated into one 32-bit word by multiply-add;
+//   * pointers are written one byte per cell, step-major, so every warp store is one
+//     contiguous 32*C byte segment;
+//   * the traceback runs in the same kernel right after the pair's fill: the warp prefetches
+//     a 32x32 tile of pointer bytes around the current cell into shared memory with 32
+//     independent loads per lane, one lane walks inside the tile, repeat.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace tanw {
 
-constexpr int      kShift   = 6;                 // fixed point: value << 6
-constexpr int      kTagM    = 0x2A;              // 10 10 10 : "came from M" in all three fields
-constexpr int      kTagX    = 0x15;              // 01 01 01 : "came from X"
-constexpr int      kTagMask = 0x3F;              //            "came from Y" is 0
+constexpr int      kShift   = 2;                 // fixed point: value << 2
+constexpr int      kTagM    = 2;                 // "came from M"
+constexpr int      kTagX    = 1;                 // "came from X"; "came from Y" is 0
+constexpr int      kTagMask = 3;
 constexpr int      kNeg     = -(1 << 30);        // stands in for -1e100 (textSeqCompare.py:55,:60)
-constexpr int      kMaxC    = 32;                // widest strip (columns per lane)
+#ifndef TANW_MAXC
+#define TANW_MAXC 16
+#endif
+constexpr int      kMaxC    = TANW_MAXC;         // widest strip (columns per lane), multiple of 4
 constexpr int      kPassW   = 32 * kMaxC;        // columns of a full pass
 constexpr int      kWarpsPerBlock = 4;
 constexpr unsigned kFull    = 0xFFFFFFFFu;
+constexpr int      kTileStride = 9;              // words per tile row in shared memory (8 + pad)
 
 struct KParams {
-    int maT, miT;            // (match<<6)|kTagM, (mismatch<<6)|kTagM
-    int ox, ex, oy, ey;      // (gox+gex)<<6, gex<<6, (goy+gey)<<6, gey<<6
-    int bg;                  // boundary_gap<<6 (module-level gap_extend, textSeqCompare.py:9)
+    int maT, miT;            // (match<<2)|kTagM, (mismatch<<2)|kTagM
+    int ox, ex, oy, ey;      // (gox+gex)<<2, gex<<2, (goy+gey)<<2, gey<<2
+    int bg;                  // boundary_gap<<2 (module-level gap_extend, textSeqCompare.py:9)
     int subst_k;
-    const int *subst;        // device table, entry = (score<<6)|kTagM, or nullptr
-    int cy[kMaxC];           // oy - ey*k
-    int ye[kMaxC];           // ey*k
+    const int *subst;        // device table, entry = (score<<2)|kTagM, or nullptr
 };
 
 struct PairDesc {
@@ -83,70 +88,78 @@ __host__ __device__ inline long long ptr_bytes(int n, int m)
     return steps * 32 * ((long long)nfull * kMaxC + (r ? remainder_c(r) : 0));
 }
 
+// Bitwise cleaning of the tag bits as opaque asm: the pointer extraction below computes
+// (raw - clean) on the IMAD pipe, and the compiler must not fold that back into (raw & 3),
+// which would put it on the already saturated alu pipe.
+__device__ __forceinline__ int clean_tag(int v)
+{
+    int r;
+    asm("and.b32 %0, %1, 0xFFFFFFFC;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ int clean_tag_or(int v, int tag)
+{
+    int r;
+    asm("lop3.b32 %0, %1, 0xFFFFFFFC, %2, 0xEA;" : "=r"(r) : "r"(v), "r"(tag));   // (v & ~3) | tag
+    return r;
+}
+
 template <int C>
 struct Strip {
-    int      W[C];        // max(M|tagM, Y) of the row above, real value
-    int      Xh[C];       // X^ = (X|tagX) - ex*i of the row above
-    int      D[C];        // max(M, X, Y) tagged, of the row above
-    unsigned ow[C / 4];   // the strip's OCR symbols, four per register
+    int W[C];         // max(M|tagM, Y) of the row above, real value
+    int Xh[C];        // X^ = (X|tagX) - ex*i of the row above
+    int D[C];         // max(M, X, Y) tagged, of the row above
+    int oc[C];        // the strip's OCR symbols
 };
 
 // One row of one strip: C cells.  See the file header for the value encoding.
 //   q_in, y_in : Q = max(M,X) tagged and Y (clean) of the cell left of the strip, same row
 //   dul_in     : D of the cell up-left of the strip's first cell
+//   xe, cx     : ex*i and ox - ex*i for this lane's row i
 // Returns the strip's right edge in q_out / y_out and the C pointer bytes in pw[C/4].
-template <int C, bool FINAL, bool SUBST>
-__device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tch, int i,
+// EYZ: gap_extend_y == 0 (the reference's default_sys), which saves the Y + ey add.
+template <int C, bool FINAL, bool SUBST, bool EYZ>
+__device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tch, int xe, int cx,
                                           int q_in, int y_in, int dul_in,
                                           int &q_out, int &y_out, unsigned (&pw)[C / 4],
                                           int kfin, int (&cap)[3])
 {
-    const int xe = kp.ex * i;                 // X = X^ + xe
-    const int cx = kp.ox - xe;                // W + ox - ex*i
-    const unsigned trep = (unsigned)tch * 0x01010101u;
     const int *srow = SUBST ? kp.subst + tch * kp.subst_k : nullptr;
     int q = q_in;
-    int yh = y_in + kp.ey;                    // Y^ of column "-1" of the strip
+    int ypl = EYZ ? y_in : y_in + kp.ey;      // Y of the column to the left, + ey
     int dul = dul_in;
-    unsigned bytes[4];
+    int acc = 0;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         int sc;
-        if (SUBST) {
-            unsigned oc = (s.ow[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            sc = __ldg(srow + oc);
-        } else {
-            unsigned x = s.ow[k >> 2] ^ trep;
-            sc = ((x & (0xFFu << (8 * (k & 3)))) == 0u) ? kp.maT : kp.miT;   // :31-32
-        }
-        // M[i][j] = max(M,X,Y)[i-1][j-1] + score, tagged as an M value   (:70-72)
-        const int m2 = (dul & ~kTagMask) + sc;
-        // X[i][j] = max(M[i-1][j]+ox, X[i-1][j]+ex, Y[i-1][j]+ox)         (:83-88)
+        if (SUBST) sc = __ldg(srow + s.oc[k]);
+        else       sc = (s.oc[k] == tch) ? kp.maT : kp.miT;                      // :31-32
+        // M[i][j] = max(M,X,Y)[i-1][j-1] + score, tagged as an M value         (:70-72)
+        const int dc = clean_tag(dul);
+        const int m2 = dc + sc;
+        // X[i][j] = max(M[i-1][j]+ox, X[i-1][j]+ex, Y[i-1][j]+ox)               (:83-88)
         const int xraw = __viaddmax_s32(s.W[k], cx, s.Xh[k]);
-        const int xh = (xraw & ~kTagMask) | kTagX;
-        // Y[i][j] = max(M[i][j-1]+oy, X[i][j-1]+oy, Y[i][j-1]+ey)         (:75-80)
-        const int yraw = __viaddmax_s32(q, kp.cy[k], yh);
-        const int yc = yraw & ~kTagMask;
-        const int w  = __viaddmax_s32(yc, kp.ye[k], m2);     // max(M, Y)
+        const int xh = clean_tag_or(xraw, kTagX);
+        // Y[i][j] = max(M[i][j-1]+oy, X[i][j-1]+oy, Y[i][j-1]+ey)               (:75-80)
+        const int yraw = __viaddmax_s32(q, kp.oy, ypl);
+        const int yc = clean_tag(yraw);
+        const int w  = max(yc, m2);                          // max(M, Y)
         const int qn = __viaddmax_s32(xh, xe, m2);           // max(M, X)
-        const int dn = __viaddmax_s32(xh, xe, w);            // max(M, X, Y)
-        // pointer byte: bits 0-1 from D(up-left), 2-3 from xraw, 4-5 (and garbage 6-7) from yraw
-        const unsigned t2 = ((unsigned)xraw & 0x0Cu) | ((unsigned)yraw & ~0x0Cu);
-        bytes[k & 3] = ((unsigned)dul & 0x03u) | (t2 & ~0x03u);
+        const int dn = max(qn, yc);                          // max(M, X, Y)
+        // pointer byte = tagM + 4*tagX + 16*tagY with tag = raw - clean, accumulated four
+        // cells per word by multiply-add (IMAD pipe); xraw - xh = tagX - 1, fixed below.
+        const int sh = 1 << (8 * (k & 3));
+        acc += (dul - dc) * sh + (xraw - xh) * (4 * sh) + (yraw - yc) * (16 * sh);
         if (FINAL) {
-            if (k == kfin) { cap[0] = m2; cap[1] = xh + xe; cap[2] = yc + kp.ye[k]; }
+            if (k == kfin) { cap[0] = m2; cap[1] = xh + xe; cap[2] = yc; }
         }
         dul = s.D[k];
         s.W[k] = w; s.Xh[k] = xh; s.D[k] = dn;
-        q = qn; yh = yc;
-        if ((k & 3) == 3) {
-            const unsigned lo = __byte_perm(bytes[0], bytes[1], 0x0040);
-            const unsigned hi = __byte_perm(bytes[2], bytes[3], 0x0040);
-            pw[k >> 2] = __byte_perm(lo, hi, 0x5410);
-        }
+        q = qn; ypl = EYZ ? yc : yc + kp.ey;
+        if ((k & 3) == 3) { pw[k >> 2] = (unsigned)acc + 0x04040404u; acc = 0; }
     }
     q_out = q;
-    y_out = yh + kp.ye[C - 1];
+    y_out = EYZ ? ypl : ypl - kp.ey;
 }
 
 template <int C>
@@ -168,98 +181,121 @@ __device__ __forceinline__ void store_ptr_words(uint8_t *dst, const unsigned (&p
     }
 }
 
+// Loop-carried state of a pass outside the strip registers.
+struct PassState {
+    int q_out, y_out;      // right edge of the row this lane computed last
+    int q_prev, y_prev;    // what the left neighbour sent in the previous step (row i-1)
+    int2 bnext;            // left boundary of the pass for the next step's row (used by lane 0)
+    int tnext;             // transcript symbol of the row this lane computes next
+    int xe, cx;            // ex*i and ox - ex*i of the row this lane computes next
+    const uint8_t *tp;     // &T[i] for the next step (row i+1 reads T[i])
+    const int2 *bp;        // &bnd[t+2]: next boundary row to prefetch
+    int2 *bw;              // &bnd[i+1]: where lane 31 leaves its right edge next
+    uint8_t *pst;          // pointer bytes of this lane for the next step
+};
+
+// One wavefront step of one pass.  GUARDED steps check whether the lane's row is inside
+// [1, n] (ramp-up / ramp-down) and capture the corner scores; steady steps do neither.
+template <int C, bool GUARDED, bool SUBST, bool EYZ>
+__device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KParams &kp,
+                                          int n, int t, int lane, bool has_next,
+                                          int fin_lane, int fin_k, int (&cap)[3])
+{
+    const int i = t - lane;                       // this lane's row in this step
+    int q_in = __shfl_up_sync(kFull, ps.q_out, 1);
+    int y_in = __shfl_up_sync(kFull, ps.y_out, 1);
+    if (lane == 0) { q_in = ps.bnext.x; y_in = ps.bnext.y; }
+    if (!GUARDED || t + 1 <= n) ps.bnext = __ldcg(ps.bp);       // same address in every lane
+    const int dul_in = max(ps.q_prev, ps.y_prev); // D of (i-1, left neighbour column)
+    const int tch = ps.tnext;
+    if (!GUARDED || (i >= 0 && i < n)) ps.tnext = (int)__ldg(ps.tp);     // row i+1 reads T[i]
+    if (!GUARDED || (i >= 1 && i <= n)) {
+        unsigned pw[C / 4];
+        const int kfin = (GUARDED && i == n && lane == fin_lane) ? fin_k : -1;
+        strip_row<C, GUARDED, SUBST, EYZ>(s, kp, tch, ps.xe, ps.cx, q_in, y_in, dul_in,
+                                          ps.q_out, ps.y_out, pw, kfin, cap);
+        store_ptr_words<C>(ps.pst, pw);
+        if (has_next && lane == 31) __stcg(ps.bw, make_int2(ps.q_out, ps.y_out));
+    }
+    ps.q_prev = q_in;
+    ps.y_prev = y_in;
+    ps.xe += kp.ex;
+    ps.cx -= kp.ex;
+    ps.tp += 1;
+    ps.bp += 1;
+    ps.bw += 1;
+    ps.pst += 32 * C;
+}
+
 // One pass: columns [j0, j0 + 32*C) of one pair, all n rows.
-//   first    : j0 == 0 (left boundary is column 0 of the matrices, textSeqCompare.py:53-56)
-//   has_next : another pass follows; lane 31 leaves its right edge in bnd[1..n]
+//   bnd      : bnd[i], i = 1..n: (Q, Y) of the column left of the pass, row i -- column 0 of
+//              the matrices for the first pass (written by the caller, textSeqCompare.py:53-56),
+//              the previous pass's right edge otherwise.  If has_next, lane 31 overwrites
+//              bnd[i] with this pass's right edge 31 steps after lane 0 consumed it.
 //   ptr      : base of this pass's pointer bytes, laid out [step t][lane][C]
 //   fin_lane, fin_k : where column m lives in this pass (or fin_lane = -1)
-template <int C, bool SUBST>
+template <int C, bool SUBST, bool EYZ>
 __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__restrict__ T,
-                                       const uint8_t *__restrict__ O, int n, int m, int j0,
-                                       bool first, bool has_next, int2 *bnd,
-                                       uint8_t *__restrict__ ptr, int fin_lane, int fin_k,
-                                       int (&cap)[3])
+                                          const uint8_t *__restrict__ O, int n, int m, int j0,
+                                          bool has_next, int2 *bnd,
+                                          uint8_t *__restrict__ ptr, int fin_lane, int fin_k,
+                                          int (&cap)[3])
 {
     const int lane = threadIdx.x & 31;
     const int c0 = j0 + lane * C;                 // 0-based first column of the strip
     Strip<C> s;
 #pragma unroll
-    for (int w = 0; w < C / 4; ++w) {
-        unsigned v = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int c = c0 + 4 * w + b;
-            const unsigned ch = (c < m) ? (unsigned)__ldg(O + c) : 0xFFu;
-            v |= ch << (8 * b);
-        }
-        s.ow[w] = v;
-    }
-    // row 0: M[0][j] = X[0][j] = bg*j, Y[0][j] = -inf   (textSeqCompare.py:57-60)
-#pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int base = kp.bg * (c0 + k + 1);
+        const int c = c0 + k;
+        s.oc[k] = (c < m) ? (int)__ldg(O + c) : 0x100;       // 0x100 never equals a symbol
+        if (SUBST && c >= m) s.oc[k] = 0;
+        // row 0: M[0][j] = X[0][j] = bg*j, Y[0][j] = -inf   (textSeqCompare.py:57-60)
+        const int base = kp.bg * (c + 1);
         s.W[k] = base | kTagM;
         s.Xh[k] = base | kTagX;
         s.D[k] = base | kTagM;
     }
-    int q_out = (kp.bg * (c0 + C)) | kTagM;       // right edge of row 0
-    int y_out = kNeg;
-    int q_prev = (kp.bg * c0) | kTagM;            // left neighbour column, row 0
-    int y_prev = kNeg;                            // (Y[0][j] = -inf, also at j = 0)
-    int2 bnext = make_int2(0, 0);
-    if (!first && lane == 0 && n >= 1) bnext = __ldcg(bnd + 1);
-    int tnext = (lane == 0 && n >= 1) ? (int)__ldg(T) : 0;   // symbol of row i+1 for this lane
+    PassState ps;
+    ps.q_out = (kp.bg * (c0 + C)) | kTagM;        // right edge of row 0
+    ps.y_out = kNeg;
+    ps.q_prev = (kp.bg * c0) | kTagM;             // left neighbour column, row 0
+    ps.y_prev = kNeg;                             // (Y[0][j] = -inf, also at j = 0)
+    ps.bnext = __ldcg(bnd + 1);
+    ps.bp = bnd + 2;
+    ps.bw = bnd + (1 - lane);
+    ps.tnext = (lane == 0) ? (int)__ldg(T) : 0;
+    ps.tp = T + (1 - lane);
+    ps.xe = kp.ex * (1 - lane);                   // row i = t - lane at t = 1
+    ps.cx = kp.ox - ps.xe;
+    ps.pst = ptr + ((size_t)32 + lane) * C;       // step t = 1
 
     const int last_step = n + 31;
-    for (int t = 1; t <= last_step; ++t) {
-        const int i = t - lane;                   // this lane's row in this step
-        int q_in = __shfl_up_sync(kFull, q_out, 1);
-        int y_in = __shfl_up_sync(kFull, y_out, 1);
-        if (lane == 0) {
-            if (first) {                          // column 0: M = Y = bg*i, X = -inf (:54-56)
-                q_in = (kp.bg * i) | kTagM;
-                y_in = kp.bg * i;
-            } else {
-                q_in = bnext.x;
-                y_in = bnext.y;
-                if (t + 1 <= n) bnext = __ldcg(bnd + t + 1);
-            }
-        }
-        const int dul_in = max(q_prev, y_prev);   // D of (i-1, left neighbour column)
-        const int tch = tnext;
-        if (i >= 0 && i < n) tnext = (int)__ldg(T + i);       // row i+1 reads T[i]
-        if (i >= 1 && i <= n) {
-            unsigned pw[C / 4];
-            if (t < n) {                          // no lane is on the last row yet
-                strip_row<C, false, SUBST>(s, kp, tch, i, q_in, y_in, dul_in, q_out, y_out, pw, -1, cap);
-            } else {
-                const int kfin = (i == n && lane == fin_lane) ? fin_k : -1;
-                strip_row<C, true, SUBST>(s, kp, tch, i, q_in, y_in, dul_in, q_out, y_out, pw, kfin, cap);
-            }
-            store_ptr_words<C>(ptr + ((size_t)t * 32 + lane) * C, pw);
-            if (has_next && lane == 31) __stcg(bnd + i, make_int2(q_out, y_out));
-        }
-        q_prev = q_in;
-        y_prev = y_in;
-    }
+    const int ramp_end = min(31, last_step);
+    int t = 1;
+    for (; t <= ramp_end; ++t)                    // ramp-up: lanes join one per step
+        pass_step<C, true, SUBST, EYZ>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap);
+    for (; t <= n - 1; ++t)                       // steady state: every lane on a row in [1, n-1]
+        pass_step<C, false, SUBST, EYZ>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap);
+    for (; t <= last_step; ++t)                   // ramp-down: last row, lanes leave one per step
+        pass_step<C, true, SUBST, EYZ>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap);
 }
 
-template <bool SUBST>
+template <bool SUBST, bool EYZ>
 __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const uint8_t *T,
-                                              const uint8_t *O, int n, int m, int j0, bool first,
+                                              const uint8_t *O, int n, int m, int j0,
                                               bool has_next, int2 *bnd, uint8_t *ptr,
                                               int fin_lane, int fin_k, int (&cap)[3])
 {
+#define TANW_CASE(CC)                                                                              \
+    case CC:                                                                                       \
+        if constexpr (CC <= kMaxC)                                                                 \
+            fill_pass<CC, SUBST, EYZ>(kp, T, O, n, m, j0, has_next, bnd, ptr, fin_lane, fin_k, cap); \
+        break;
     switch (C) {
-    case 4:  fill_pass<4,  SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
-    case 8:  fill_pass<8,  SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
-    case 12: fill_pass<12, SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
-    case 16: fill_pass<16, SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
-    case 20: fill_pass<20, SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
-    case 24: fill_pass<24, SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
-    case 28: fill_pass<28, SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
-    default: fill_pass<32, SUBST>(kp, T, O, n, m, j0, first, has_next, bnd, ptr, fin_lane, fin_k, cap); break;
+        TANW_CASE(4) TANW_CASE(8) TANW_CASE(12) TANW_CASE(16)
+        TANW_CASE(20) TANW_CASE(24) TANW_CASE(28) TANW_CASE(32)
     }
+#undef TANW_CASE
 }
 
 // Address of the pointer byte of cell (i, j), 1-based, inside a pair's pointer block.
@@ -286,29 +322,61 @@ struct PtrMap {
     }
 };
 
-// Traceback of one pair by one lane (textSeqCompare.py:96-164), ops written back to front at
-// the END of the pair's op buffer (capacity n+m); returns the number of columns.
-__device__ __forceinline__ int traceback_lane(const uint8_t *ptr, int n, int m, uint8_t *ops_end)
+// Traceback of one pair (textSeqCompare.py:96-164) by one warp.  The pointer chase is a chain
+// of dependent loads, so the warp first pulls the 32x32 tile of pointer bytes whose bottom-
+// right corner is the current cell into shared memory (lane r: row x-r, 32 independent loads),
+// then lane 0 walks inside the tile.  Ops are written back to front at the END of the pair's
+// op buffer (capacity n+m); returns the number of columns (valid in every lane).
+__device__ __forceinline__ int traceback_warp(const uint8_t *ptr, int n, int m, uint8_t *ops_end,
+                                              unsigned *tile, int lane)
 {
     int x = n, y = m, k = 0;
     if (n > 0 && m > 0) {
         const PtrMap map(n, m);
-        unsigned b = __ldcg(ptr + map.offset(x, y));
-        int st = 2 - (int)(b & 3u);                      // mpt = mat_ptr[n][m]            (:102)
-        while (true) {
-            int op;
-            if (st == 0)      { op = 0; st = 2 - (int)(b & 3u);        --x; --y; }   // :115-125
-            else if (st == 1) { op = 1; st = 2 - (int)((b >> 2) & 3u); --x; }        // :128-135
-            else              { op = 2; st = 2 - (int)((b >> 4) & 3u); --y; }        // :138-145
-            ++k;
-            *(ops_end - k) = (uint8_t)op;
-            if (x <= 0 || y <= 0) break;
-            b = __ldcg(ptr + map.offset(x, y));
+        int st = -1;                                       // -1: take mat_ptr[n][m] first (:102)
+        while (x > 0 && y > 0) {
+            // ---- tile load: rows x-lane, columns y-31 .. y ---------------------------------
+            const int row = x - lane;
+            unsigned words[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) words[w] = 0;
+            if (row >= 1) {
+                unsigned v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int col = y - c;
+                    v[c] = (col >= 1) ? (unsigned)__ldcg(ptr + map.offset(row, col)) : 0u;
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) words[c >> 2] |= v[c] << (8 * (c & 3));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tile[lane * kTileStride + w] = words[w];
+            __syncwarp();
+            // ---- walk inside the tile -----------------------------------------------------
+            if (lane == 0) {
+                int r = 0, c = 0;
+                while (r < 32 && c < 32 && x > 0 && y > 0) {
+                    const unsigned b = (tile[r * kTileStride + (c >> 2)] >> (8 * (c & 3))) & 0xFFu;
+                    if (st < 0) st = 2 - (int)(b & 3u);                               // :102
+                    int op;
+                    if (st == 0)      { op = 0; st = 2 - (int)(b & 3u);        --x; --y; ++r; ++c; }  // :115-125
+                    else if (st == 1) { op = 1; st = 2 - (int)((b >> 2) & 3u); --x; ++r; }            // :128-135
+                    else              { op = 2; st = 2 - (int)((b >> 4) & 3u); --y; ++c; }            // :138-145
+                    ++k;
+                    *(ops_end - k) = (uint8_t)op;
+                }
+            }
+            x = __shfl_sync(kFull, x, 0);
+            y = __shfl_sync(kFull, y, 0);
         }
     }
-    while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // OCR remainder first          (:154-158)
-    while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // then transcript remainder    (:160-164)
-    return k;
+    if (lane == 0) {
+        while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // OCR remainder first       (:154-158)
+        while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // then transcript remainder (:160-164)
+    }
+    return __shfl_sync(kFull, k, 0);
 }
 
 __device__ __forceinline__ int score_out(int v)
@@ -316,12 +384,17 @@ __device__ __forceinline__ int score_out(int v)
     return (v <= kNeg / 2) ? kNeg : (v >> kShift);
 }
 
-template <bool SUBST>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+#ifndef TANW_MINB
+#define TANW_MINB 4
+#endif
+template <bool SUBST, bool EYZ>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
 {
+    __shared__ unsigned tiles[kWarpsPerBlock][32 * kTileStride];
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * kWarpsPerBlock + warp;
     uint8_t *const ptr = a.ptr_arena + (size_t)slot * (size_t)a.slot_bytes;
     int2 *const bnd = a.bnd_arena + (size_t)slot * (size_t)a.bnd_rows;
 
@@ -346,6 +419,10 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
             const int nfull = m / kPassW, r = m % kPassW;
             const int npass = nfull + (r ? 1 : 0);
             const long long pass_bytes = ((long long)n + 32) * kPassW;
+            // left boundary of the first pass = column 0: M = Y = bg*i, X = -inf   (:54-56)
+            for (int i = 1 + lane; i <= n + 1; i += 32)
+                __stcg(bnd + i, make_int2((kp.bg * i) | kTagM, kp.bg * i));
+            __syncwarp();
             for (int ps = 0; ps < npass; ++ps) {
                 const int C = (ps < nfull) ? kMaxC : remainder_c(r);
                 const int j0 = ps * kPassW;
@@ -353,8 +430,8 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
                 const int cc = m - 1 - j0;
                 const int fin_lane = last ? cc / C : -1;
                 const int fin_k = last ? cc % C : -1;
-                dispatch_pass<SUBST>(C, kp, T, O, n, m, j0, ps == 0, !last, bnd,
-                                     ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap);
+                dispatch_pass<SUBST, EYZ>(C, kp, T, O, n, m, j0, !last, bnd,
+                                          ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap);
                 __syncwarp();
             }
             // the lane that owns column m holds the corner scores
@@ -365,9 +442,8 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
         }
         __syncwarp();
         uint8_t *ops = a.ops + pd.ops_off;
-        int L = 0;
+        const int L = traceback_warp(ptr, n, m, ops + (size_t)n + (size_t)m, tiles[warp], lane);
         if (lane == 0) {
-            L = traceback_lane(ptr, n, m, ops + (size_t)n + (size_t)m);
             a.ops_len[p] = L;
             if (a.scores) {
                 a.scores[3 * (size_t)p + 0] = score_out(cap[0]);
@@ -375,7 +451,6 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
                 a.scores[3 * (size_t)p + 2] = score_out(cap[2]);
             }
         }
-        L = __shfl_sync(kFull, L, 0);
         // move the op string from the end of the buffer to its start (left to right order)
         const int shift = n + m - L;
         if (shift > 0) {
