@@ -101,6 +101,11 @@ int  tanw_create(int device, tanw_ctx **out);
 int  tanw_destroy(tanw_ctx *ctx);
 /* Upper bound for the traceback-pointer arena in bytes (0 = default: 40% of device memory). */
 int  tanw_set_arena_limit(tanw_ctx *ctx, int64_t bytes);
+/* Pairs with n*m >= cells take the chained-pass path: one warp per 512-column stripe, all
+ * stripes resident at once (cooperative launch), so that a single whole-manuscript pair
+ * (BASELINE config 5, 100k x 80k) uses the whole GPU.  Default 2^26.  Results are identical
+ * on both paths; the threshold only moves work between them. */
+int  tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells);
 
 /* ---- one-call batch alignment: the entry the reference's call site maps to ------------------
  * Replaces N calls of textSeqCompare.perform_alignment (textSeqCompare.py:13) -- copies the

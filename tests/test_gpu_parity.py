@@ -257,3 +257,57 @@ def test_op_string_invariants_at_scale(tsc):
         o = ops[ops_off[k]:ops_off[k] + ops_len[k]]
         assert int((o != 2).sum()) == n[k] and int((o != 1).sum()) == m[k]
         assert max(n[k], m[k]) <= o.size <= n[k] + m[k]
+
+
+# ---- whole-manuscript pairs: chained-pass path (BASELINE config 5) ------------------------------
+
+@pytest.fixture()
+def long_ctx(tsc):
+    """A private context whose long-pair threshold is 1 cell, so every pair takes the
+    chained-pass path regardless of size."""
+    from text_alignment_b200 import _native
+    ctx = _native.Context(0)
+    ctx.set_long_threshold(1)
+    yield ctx
+    ctx.close()
+
+
+def _check_ctx_vs_oracle(ctx, oracle, pairs, params=DEFAULT):
+    buf, t_off, n, o_off, m = _pack(pairs)
+    ops, ops_off, ops_len, scores = ctx.align_batch(buf, t_off, n, o_off, m, ctx.make_scoring(*params))
+    sc, _ = oracle.make_scoring(list(params[:6]), boundary_gap=params[6])
+    r_ops, r_off, r_len, r_end = oracle.align_batch_codes(buf, t_off, n, o_off, m, sc, threads=8)
+    assert ops_len.tolist() == r_len.tolist()
+    for k in range(len(pairs)):
+        assert np.array_equal(ops[ops_off[k]:ops_off[k] + ops_len[k]], r_ops[r_off[k]:r_off[k] + r_len[k]]), \
+            'pair %d (n=%d, m=%d)' % (k, n[k], m[k])
+        got = tuple(None if v == -1073741824 else int(v) for v in scores[k].tolist())
+        assert got == _end(r_end[k].tolist())
+
+
+def test_long_path_small_and_ragged(long_ctx, oracle):
+    pairs = [synth.make_pair(600 + k, n, m, 2, 30) for k, (n, m) in enumerate(
+        [(1, 1), (1, 700), (700, 1), (31, 513), (33, 511), (64, 1024), (100, 1025), (300, 1100),
+         (1500, 520), (40, 3000), (257, 2049)])]
+    _check_ctx_vs_oracle(long_ctx, oracle, pairs)
+
+
+def test_long_path_random_parameters(long_ctx, oracle):
+    rng = random.Random(31)
+    pairs = [(''.join(rng.choice('abc') for _ in range(rng.randint(1, 900))),
+              ''.join(rng.choice('abc') for _ in range(rng.randint(1, 2600)))) for _ in range(6)]
+    for params in [(5, -4, -2, -7, 0, -5, -1), (1, -1, -1, -1, -1, -1, -3), (7, 2, -4, -9, -1, 1, 0)]:
+        _check_ctx_vs_oracle(long_ctx, oracle, pairs, params)
+
+
+def test_long_and_batched_pairs_mixed(tsc, oracle):
+    """One batch holding ordinary pages and a pair above the default threshold (2^26 cells)."""
+    pairs = [synth.c2_pair(7), synth.make_pair(5002, 9000, 8000, 5, 200), synth.c3_pair(3), synth.c2_pair(8)]
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+
+
+def test_c5_whole_manuscript_pair(tsc, oracle):
+    """BASELINE config 5 at full size: n=80 000 x m=100 000 (8e9 cells), bit-exact op string and
+    corner scores against the C oracle (the Python reference would need 384 GB)."""
+    t, o = synth.c5_pair()
+    _check_packed_vs_oracle(tsc, oracle, [(t, o)], threads=1)

@@ -48,7 +48,10 @@ struct tanw_ctx {
     std::string err;
     int64_t arena_limit = 0;
 
-    DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst;
+    DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_prog;
+    std::vector<int> h_long;              // pairs routed to the chained-pass (whole-GPU) path
+    int long_capacity = 0;                // resident warps for a cooperative launch
+    int64_t long_cells = int64_t(1) << 26;   // pairs with n*m >= this use the chained-pass path
     std::vector<PairDesc> h_pairs;
     std::vector<int> h_order;
     std::vector<int64_t> h_ops_off;       // canonical device layout: prefix sums of n+m
@@ -107,6 +110,43 @@ bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
     if (s->subst)
         for (int64_t i = 0; i < (int64_t)s->subst_k * s->subst_k; ++i) upd(s->subst[i]);
     return (max_n_plus_m + 2) * pmax < (int64_t(1) << 25);
+}
+
+// One whole-manuscript pair on the chained-pass path: init, one cooperative launch per wave
+// of resident stripes, traceback.
+int run_long_pair(tanw_ctx *ctx, int p, int *launches)
+{
+    const PairDesc &pd = ctx->h_pairs[(size_t)p];
+    LongArgs la;
+    la.T = (const uint8_t *)ctx->d_sym.p + pd.t_off;
+    la.O = (const uint8_t *)ctx->d_sym.p + pd.o_off;
+    la.n = pd.n;
+    la.m = pd.m;
+    la.ptr = (uint8_t *)ctx->d_arena.p;
+    la.bnd = (int2 *)ctx->d_bnd.p;
+    la.bnd_stride = (long long)pd.n + 4;
+    la.prog = (int *)ctx->d_prog.p;
+    la.pass0 = 0;
+    la.scores = (int *)ctx->d_scores.p + 3 * (size_t)p;
+    const int npass = (pd.m + kPassW - 1) / kPassW;
+    long_init_kernel<<<std::min(64, (pd.n + 255) / 256 + 1), 256, 0, ctx->stream>>>(la, ctx->kp);
+    TANW_CUDA(ctx, cudaGetLastError());
+    ++*launches;
+    for (int w0 = 0; w0 < npass; w0 += ctx->long_capacity) {
+        la.pass0 = w0;
+        const int grid = std::min(ctx->long_capacity, npass - w0);
+        void *args[] = { (void *)&la, (void *)&ctx->kp };
+        const void *fn = ctx->use_subst ? (const void *)align_long_kernel<true, false>
+                       : (ctx->kp.ey == 0 ? (const void *)align_long_kernel<false, true>
+                                          : (const void *)align_long_kernel<false, false>);
+        TANW_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(32), args, 0, ctx->stream));
+        ++*launches;
+    }
+    trace_long_kernel<<<1, 32, 0, ctx->stream>>>(la.ptr, pd.n, pd.m, (uint8_t *)ctx->d_ops.p + pd.ops_off,
+                                                 (int *)ctx->d_len.p + p);
+    TANW_CUDA(ctx, cudaGetLastError());
+    ++*launches;
+    return TANW_OK;
 }
 
 }  // namespace
@@ -195,6 +235,13 @@ int tanw_create(int device, tanw_ctx **out)
     }
     if (ctx->occ_plain < 1) ctx->occ_plain = 1;
     if (ctx->occ_subst < 1) ctx->occ_subst = 1;
+    {
+        int occ_long = 0, coop = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, align_long_kernel<true, false>, 32, 0);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        ctx->long_capacity = coop ? std::max(1, occ_long) * ctx->sm_count : 0;
+        cudaGetLastError();
+    }
     *out = ctx;
     return TANW_OK;
 }
@@ -205,7 +252,7 @@ int tanw_destroy(tanw_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_pairs, &ctx->d_order, &ctx->d_counter, &ctx->d_arena,
-                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst };
+                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst, &ctx->d_prog };
     for (auto b : bufs) b->release();
     cudaEvent_t evs[] = { ctx->ev_h2d0, ctx->ev_h2d1, ctx->ev_k0, ctx->ev_k1, ctx->ev_d2h0, ctx->ev_d2h1 };
     for (auto ev : evs)
@@ -220,6 +267,14 @@ int tanw_set_arena_limit(tanw_ctx *ctx, int64_t bytes)
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     if (bytes < 0) return fail(ctx, TANW_E_INVALID, "arena limit must be >= 0");
     ctx->arena_limit = bytes;
+    return TANW_OK;
+}
+
+int tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    if (cells < 1) return fail(ctx, TANW_E_INVALID, "long-pair threshold must be >= 1 cell");
+    ctx->long_cells = cells;
     return TANW_OK;
 }
 
@@ -256,8 +311,9 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     // ---- pair table, canonical op layout, size statistics --------------------------------
     ctx->h_pairs.resize((size_t)n_pairs);
     ctx->h_ops_off.resize((size_t)n_pairs);
-    int64_t ops_total = 0, cells = 0, ptr_total = 0, max_nm = 0, max_slot = 0;
-    int max_n = 0;
+    ctx->h_long.clear();
+    int64_t ops_total = 0, cells = 0, ptr_total = 0, max_nm = 0, max_slot = 0, max_long = 0, max_long_bnd = 0;
+    int max_n = 0, max_long_pass = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
         const int64_t np = n[p], mp = m[p];
         if (np < 0 || mp < 0) return fail(ctx, TANW_E_INVALID, "pair %lld: negative length", (long long)p);
@@ -271,9 +327,18 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         cells += np * mp;
         const int64_t pb = ptr_bytes((int)np, (int)mp);
         ptr_total += np * mp;
-        max_slot = std::max(max_slot, pb);
         max_nm = std::max(max_nm, np + mp);
-        max_n = std::max(max_n, (int)np);
+        if (np * mp >= ctx->long_cells && ctx->long_capacity > 0) {
+            // whole-manuscript pair: one warp per column stripe, all stripes resident at once
+            ctx->h_long.push_back((int)p);
+            const int64_t npass = (mp + kPassW - 1) / kPassW;
+            max_long = std::max(max_long, pb);
+            max_long_bnd = std::max(max_long_bnd, (npass + 1) * (np + 4));
+            max_long_pass = std::max<int>(max_long_pass, (int)npass);
+        } else {
+            max_slot = std::max(max_slot, pb);
+            max_n = std::max(max_n, (int)np);
+        }
     }
     if (!scoring_in_range(sc, max_nm))
         return fail(ctx, TANW_E_RANGE,
@@ -286,8 +351,16 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     }
 
     // ---- work order: largest pairs first (greedy longest-processing-time) ------------------
-    ctx->h_order.resize((size_t)n_pairs);
-    std::iota(ctx->h_order.begin(), ctx->h_order.end(), 0);
+    ctx->h_order.clear();
+    ctx->h_order.reserve((size_t)n_pairs);
+    {
+        size_t li = 0;
+        for (int64_t p = 0; p < n_pairs; ++p) {
+            if (li < ctx->h_long.size() && ctx->h_long[li] == (int)p) { ++li; continue; }
+            ctx->h_order.push_back((int)p);
+        }
+    }
+    const int64_t n_batch = (int64_t)ctx->h_order.size();
     {
         const std::vector<PairDesc> &hp = ctx->h_pairs;
         std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&hp](int a, int b) {
@@ -312,7 +385,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     // ---- launch geometry and scratch ----------------------------------------------------------
     const int occ = ctx->use_subst ? ctx->occ_subst : ctx->occ_plain;
     int grid = ctx->sm_count * occ;
-    const int64_t need_blocks = (n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t need_blocks = (n_batch + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (need_blocks < grid) grid = (int)std::max<int64_t>(need_blocks, 1);
     const int64_t slot_bytes = (max_slot + 255) / 256 * 256;
     int64_t limit = ctx->arena_limit;
@@ -321,6 +394,9 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         TANW_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
         limit = (int64_t)(tot / 10 * 4);
     }
+    if (max_long > (int64_t)(limit / 4 * 9))
+        return fail(ctx, TANW_E_NOMEM, "a pair needs %lld bytes of traceback pointers; arena limit is %lld",
+                    (long long)max_long, (long long)limit);
     if (slot_bytes > 0) {
         int64_t max_blocks = limit / (slot_bytes * kWarpsPerBlock);
         if (max_blocks < 1)
@@ -338,8 +414,9 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         ctx->d_pairs.reserve(sizeof(PairDesc) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_order.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_counter.reserve(256) != cudaSuccess ||
-        ctx->d_arena.reserve((size_t)std::max<int64_t>(slots * slot_bytes, 256)) != cudaSuccess ||
-        ctx->d_bnd.reserve(sizeof(int2) * (size_t)(slots * bnd_rows)) != cudaSuccess ||
+        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(slots * slot_bytes, max_long), 256)) != cudaSuccess ||
+        ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(slots * bnd_rows, max_long_bnd)) != cudaSuccess ||
+        ctx->d_prog.reserve(sizeof(int) * (size_t)(max_long_pass + 2)) != cudaSuccess ||
         ctx->d_ops.reserve((size_t)ops_total + 64) != cudaSuccess ||
         ctx->d_len.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_scores.reserve(sizeof(int) * 3 * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess) {
@@ -355,9 +432,10 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     if (n_pairs > 0) {
         TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairDesc) * (size_t)n_pairs,
                                        cudaMemcpyHostToDevice, ctx->stream));
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * (size_t)n_pairs,
-                                       cudaMemcpyHostToDevice, ctx->stream));
-        h2d += (int64_t)(sizeof(PairDesc) + sizeof(int)) * n_pairs;
+        if (n_batch > 0)
+            TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * (size_t)n_batch,
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        h2d += (int64_t)sizeof(PairDesc) * n_pairs + (int64_t)sizeof(int) * n_batch;
     }
     if (ctx->use_subst) {
         const size_t kk = (size_t)sc->subst_k * (size_t)sc->subst_k;
@@ -378,7 +456,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     a.pairs = (const PairDesc *)ctx->d_pairs.p;
     a.order = (const int *)ctx->d_order.p;
     a.counter = (unsigned *)ctx->d_counter.p;
-    a.n_pairs = (int)n_pairs;
+    a.n_pairs = (int)n_batch;
     a.ptr_arena = (uint8_t *)ctx->d_arena.p;
     a.slot_bytes = slot_bytes;
     a.bnd_arena = (int2 *)ctx->d_bnd.p;
@@ -404,7 +482,7 @@ int tanw_batch_run(tanw_ctx *ctx)
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     int launches = 0;
-    if (ctx->n_pairs > 0) {
+    if (ctx->args.n_pairs > 0) {
         TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned), ctx->stream));
         // three instantiations: tabulated scorer; equality scorer; equality scorer with
         // gap_extend_y == 0 (the reference's default_sys), which drops one add per cell
@@ -416,6 +494,10 @@ int tanw_batch_run(tanw_ctx *ctx)
             align_pairs_kernel<false, false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
         TANW_CUDA(ctx, cudaGetLastError());
         launches = 1;
+    }
+    for (int p : ctx->h_long) {
+        int rc = run_long_pair(ctx, p, &launches);
+        if (rc) return rc;
     }
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
     ctx->timing.kernel_launches = launches;

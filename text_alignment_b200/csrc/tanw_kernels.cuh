@@ -192,20 +192,41 @@ struct PassState {
     const int2 *bp;        // &bnd[t+2]: next boundary row to prefetch
     int2 *bw;              // &bnd[i+1]: where lane 31 leaves its right edge next
     uint8_t *pst;          // pointer bytes of this lane for the next step
+    int avail;             // chained passes: rows of the left boundary known to be published
 };
+
+// Chained passes (one huge pair spread over many warps): pass w publishes how many rows of its
+// right edge are visible in prog_out; pass w+1 polls it before prefetching a boundary row.
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+constexpr int kPublishEvery = 32;      // rows between two progress publications
 
 // One wavefront step of one pass.  GUARDED steps check whether the lane's row is inside
 // [1, n] (ramp-up / ramp-down) and capture the corner scores; steady steps do neither.
-template <int C, bool GUARDED, bool SUBST, bool EYZ>
+template <int C, bool GUARDED, bool SUBST, bool EYZ, bool CHAINED>
 __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KParams &kp,
                                           int n, int t, int lane, bool has_next,
-                                          int fin_lane, int fin_k, int (&cap)[3])
+                                          int fin_lane, int fin_k, int (&cap)[3],
+                                          const int *prog_in, int *prog_out)
 {
     const int i = t - lane;                       // this lane's row in this step
     int q_in = __shfl_up_sync(kFull, ps.q_out, 1);
     int y_in = __shfl_up_sync(kFull, ps.y_out, 1);
     if (lane == 0) { q_in = ps.bnext.x; y_in = ps.bnext.y; }
-    if (!GUARDED || t + 1 <= n) ps.bnext = __ldcg(ps.bp);       // same address in every lane
+    if (!GUARDED || t + 1 <= n) {
+        if (CHAINED) {                            // warp-uniform spin on the producer's progress
+            while (ps.avail < t + 1) ps.avail = ld_acquire(prog_in);
+        }
+        ps.bnext = __ldcg(ps.bp);                 // same address in every lane
+    }
     const int dul_in = max(ps.q_prev, ps.y_prev); // D of (i-1, left neighbour column)
     const int tch = ps.tnext;
     if (!GUARDED || (i >= 0 && i < n)) ps.tnext = (int)__ldg(ps.tp);     // row i+1 reads T[i]
@@ -215,7 +236,13 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
         strip_row<C, GUARDED, SUBST, EYZ>(s, kp, tch, ps.xe, ps.cx, q_in, y_in, dul_in,
                                           ps.q_out, ps.y_out, pw, kfin, cap);
         store_ptr_words<C>(ps.pst, pw);
-        if (has_next && lane == 31) __stcg(ps.bw, make_int2(ps.q_out, ps.y_out));
+        if (has_next && lane == 31) {
+            __stcg(ps.bw, make_int2(ps.q_out, ps.y_out));
+            if (CHAINED && ((i & (kPublishEvery - 1)) == 0 || i == n)) {
+                __threadfence();
+                st_release(prog_out, i);
+            }
+        }
     }
     ps.q_prev = q_in;
     ps.y_prev = y_in;
@@ -234,12 +261,12 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
 //              bnd[i] with this pass's right edge 31 steps after lane 0 consumed it.
 //   ptr      : base of this pass's pointer bytes, laid out [step t][lane][C]
 //   fin_lane, fin_k : where column m lives in this pass (or fin_lane = -1)
-template <int C, bool SUBST, bool EYZ>
+template <int C, bool SUBST, bool EYZ, bool CHAINED>
 __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__restrict__ T,
                                           const uint8_t *__restrict__ O, int n, int m, int j0,
-                                          bool has_next, int2 *bnd,
+                                          bool has_next, const int2 *bnd, int2 *bnd_out,
                                           uint8_t *__restrict__ ptr, int fin_lane, int fin_k,
-                                          int (&cap)[3])
+                                          int (&cap)[3], const int *prog_in, int *prog_out)
 {
     const int lane = threadIdx.x & 31;
     const int c0 = j0 + lane * C;                 // 0-based first column of the strip
@@ -260,9 +287,13 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     ps.y_out = kNeg;
     ps.q_prev = (kp.bg * c0) | kTagM;             // left neighbour column, row 0
     ps.y_prev = kNeg;                             // (Y[0][j] = -inf, also at j = 0)
+    ps.avail = 0;
+    if (CHAINED) {
+        while (ps.avail < 1) ps.avail = ld_acquire(prog_in);
+    }
     ps.bnext = __ldcg(bnd + 1);
     ps.bp = bnd + 2;
-    ps.bw = bnd + (1 - lane);
+    ps.bw = bnd_out + (1 - lane);
     ps.tnext = (lane == 0) ? (int)__ldg(T) : 0;
     ps.tp = T + (1 - lane);
     ps.xe = kp.ex * (1 - lane);                   // row i = t - lane at t = 1
@@ -273,23 +304,25 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     const int ramp_end = min(31, last_step);
     int t = 1;
     for (; t <= ramp_end; ++t)                    // ramp-up: lanes join one per step
-        pass_step<C, true, SUBST, EYZ>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap);
+        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, prog_in, prog_out);
     for (; t <= n - 1; ++t)                       // steady state: every lane on a row in [1, n-1]
-        pass_step<C, false, SUBST, EYZ>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap);
+        pass_step<C, false, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, prog_in, prog_out);
     for (; t <= last_step; ++t)                   // ramp-down: last row, lanes leave one per step
-        pass_step<C, true, SUBST, EYZ>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap);
+        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, prog_in, prog_out);
 }
 
-template <bool SUBST, bool EYZ>
+template <bool SUBST, bool EYZ, bool CHAINED>
 __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const uint8_t *T,
                                               const uint8_t *O, int n, int m, int j0,
-                                              bool has_next, int2 *bnd, uint8_t *ptr,
-                                              int fin_lane, int fin_k, int (&cap)[3])
+                                              bool has_next, const int2 *bnd, int2 *bnd_out,
+                                              uint8_t *ptr, int fin_lane, int fin_k, int (&cap)[3],
+                                              const int *prog_in, int *prog_out)
 {
 #define TANW_CASE(CC)                                                                              \
     case CC:                                                                                       \
         if constexpr (CC <= kMaxC)                                                                 \
-            fill_pass<CC, SUBST, EYZ>(kp, T, O, n, m, j0, has_next, bnd, ptr, fin_lane, fin_k, cap); \
+            fill_pass<CC, SUBST, EYZ, CHAINED>(kp, T, O, n, m, j0, has_next, bnd, bnd_out, ptr,     \
+                                               fin_lane, fin_k, cap, prog_in, prog_out);            \
         break;
     switch (C) {
         TANW_CASE(4) TANW_CASE(8) TANW_CASE(12) TANW_CASE(16)
@@ -430,8 +463,9 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
                 const int cc = m - 1 - j0;
                 const int fin_lane = last ? cc / C : -1;
                 const int fin_k = last ? cc % C : -1;
-                dispatch_pass<SUBST, EYZ>(C, kp, T, O, n, m, j0, !last, bnd,
-                                          ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap);
+                dispatch_pass<SUBST, EYZ, false>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
+                                                 ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap,
+                                                 nullptr, nullptr);
                 __syncwarp();
             }
             // the lane that owns column m holds the corner scores
@@ -464,6 +498,83 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
             }
         }
         __syncwarp();
+    }
+}
+
+// ---- one huge pair: chained passes ---------------------------------------------------------------
+// BASELINE config 5 (100k x 80k): a single pair must use the whole GPU.  Every pass (a stripe
+// of 32*C columns) gets its own warp, all passes are resident at once (cooperative launch), and
+// pass w consumes the right edge of pass w-1 through global memory about kPublishEvery rows
+// behind it -- a wavefront over stripes.  Pointers for the whole matrix stay in HBM
+// (1 byte/cell; 8 GB for config 5), and the ordinary tile-prefetch traceback runs afterwards.
+struct LongArgs {
+    const uint8_t *T, *O;
+    int n, m;
+    uint8_t *ptr;          // ptr_bytes(n, m)
+    int2 *bnd;             // (npass + 1) arrays of bnd_stride entries; array w = left edge of pass w
+    long long bnd_stride;
+    int *prog;             // npass + 1 progress counters; prog[0] = n once column 0 is written
+    int pass0;             // first pass handled by this launch (waves when passes > resident warps)
+    int *scores;           // 3 ints
+};
+
+__global__ void __launch_bounds__(256) long_init_kernel(const LongArgs a, const __grid_constant__ KParams kp)
+{
+    // left boundary of pass 0 = column 0: M = Y = bg*i, X = -inf (textSeqCompare.py:54-56)
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = 1 + blockIdx.x * blockDim.x + threadIdx.x; i <= a.n + 1; i += stride)
+        a.bnd[i] = make_int2((kp.bg * i) | kTagM, kp.bg * i);
+    const int npass = (a.m + kPassW - 1) / kPassW;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w <= npass; w += stride)
+        a.prog[w] = (w == 0) ? a.n : 0;       // column 0 is complete when this kernel ends
+}
+
+template <bool SUBST, bool EYZ>
+__global__ void __launch_bounds__(32, 8)
+align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
+{
+    const int w = a.pass0 + blockIdx.x;
+    const int n = a.n, m = a.m;
+    const int nfull = m / kPassW, r = m % kPassW;
+    const int npass = nfull + (r ? 1 : 0);
+    if (w >= npass) return;
+    const int C = (w < nfull) ? kMaxC : remainder_c(r);
+    const int j0 = w * kPassW;
+    const bool last = (w == npass - 1);
+    const int cc = m - 1 - j0;
+    const int fin_lane = last ? cc / C : -1;
+    const int fin_k = last ? cc % C : -1;
+    int cap[3] = {0, 0, 0};
+    const long long pass_bytes = ((long long)n + 32) * kPassW;
+    dispatch_pass<SUBST, EYZ, true>(C, kp, a.T, a.O, n, m, j0, !last,
+                                    a.bnd + (size_t)w * (size_t)a.bnd_stride,
+                                    a.bnd + (size_t)(w + 1) * (size_t)a.bnd_stride,
+                                    a.ptr + (size_t)w * (size_t)pass_bytes, fin_lane, fin_k, cap,
+                                    a.prog + w, a.prog + w + 1);
+    if (last && (int)(threadIdx.x & 31) == fin_lane && a.scores) {
+        a.scores[0] = score_out(cap[0]);
+        a.scores[1] = score_out(cap[1]);
+        a.scores[2] = score_out(cap[2]);
+    }
+}
+
+__global__ void __launch_bounds__(32)
+trace_long_kernel(const uint8_t *ptr, int n, int m, uint8_t *ops, int *ops_len)
+{
+    __shared__ unsigned tile[32 * kTileStride];
+    const int lane = threadIdx.x & 31;
+    const int L = traceback_warp(ptr, n, m, ops + (size_t)n + (size_t)m, tile, lane);
+    if (lane == 0) *ops_len = L;
+    const int shift = n + m - L;
+    if (shift > 0) {
+        for (int base = 0; base < L; base += 32) {
+            const int q = base + lane;
+            uint8_t v = 0;
+            if (q < L) v = __ldcg(ops + shift + q);
+            __syncwarp();
+            if (q < L) ops[q] = v;
+            __syncwarp();
+        }
     }
 }
 
