@@ -54,6 +54,10 @@ def measured_peaks():
 def _gen_one(args):
     from text_alignment_b200 import synth
     which, k = args
+    if which == 'c1':
+        return synth.c1_page()
+    if which == 'c5':
+        return synth.c5_pair()
     return getattr(synth, which + '_pair')(k)
 
 
@@ -82,9 +86,13 @@ def pack_pairs(pairs):
 WORKLOADS = {
     'c2': dict(name='config 2: seeded synthetic page pairs, n~U[1000,1600], m=1.25n, 20% sub + 5% indel, runs 5-40',
                default_pairs=10000),
-    'c3': dict(name='config 3: seeded synthetic line pairs, n,m~U[40,120], runs 2-6', default_pairs=200000),
+    'c1': dict(name='config 1: single Salzinnes-shaped page, seed 1001, n=1200, m=1500', default_pairs=1),
+    'c3': dict(name='config 3: seeded synthetic line pairs, n,m~U[40,120], runs 2-6 (1M pairs over 8 GPUs)',
+               default_pairs=125000),
     'c4': dict(name='config 4: St. Gall-shaped pages, n~U[600,1000], m=n*U[2,4], inserted runs 50-400',
                default_pairs=4096),
+    'c5': dict(name='config 5: whole-manuscript pair, seed 5001, n=80000 x m=100000 (chained-pass path)',
+               default_pairs=1),
 }
 
 
@@ -241,6 +249,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--out', default='', help='also write the JSON line to this file')
     ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU per step (default: the config size)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--parity-pairs', type=int, default=16)
@@ -280,6 +289,8 @@ def main():
 
     # ---- parity spot check against the oracle (outside every timed region) ----------------------
     parity = 0
+    if args.workload == 'c5':
+        args.parity_pairs = 0      # 8e9 cells: checked by tests/test_gpu_parity.py::test_c5_whole_manuscript_pair
     if args.parity_pairs > 0:
         from oracle import nw_oracle
         k = min(args.parity_pairs, npairs)
@@ -414,6 +425,9 @@ def main():
             line['cpu_baseline_c'] = dict(value=k_cells / k_wall / 1e9, unit='GCUPS', cores=cores, kind='port',
                                           sample='%d full pages, oracle/nw_oracle.c (scalar C, float64), %d threads' % (k, cores))
         print(json.dumps(line))
+        if args.out:
+            with open(args.out, 'w') as f:
+                json.dump(line, f, indent=1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -88,6 +88,8 @@ typedef struct tanw_timing {
     int64_t cells;         /* sum of n*m over the batch                                        */
     int64_t ptr_bytes;     /* traceback-pointer bytes the fill kernel writes (algorithmic)     */
     int64_t h2d_bytes, d2h_bytes;
+    /* host wall-clock spent inside the three phases (includes the waits on the device) */
+    float   host_prepare_ms, host_run_ms, host_fetch_ms;
 } tanw_timing;
 
 /* ---- library / device queries ------------------------------------------------------------ */

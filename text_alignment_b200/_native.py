@@ -33,7 +33,9 @@ class DeviceInfo(ctypes.Structure):
 class Timing(ctypes.Structure):
     _fields_ = [('h2d_ms', ctypes.c_float), ('kernel_ms', ctypes.c_float), ('d2h_ms', ctypes.c_float),
                 ('kernel_launches', ctypes.c_int32), ('cells', ctypes.c_int64), ('ptr_bytes', ctypes.c_int64),
-                ('h2d_bytes', ctypes.c_int64), ('d2h_bytes', ctypes.c_int64)]
+                ('h2d_bytes', ctypes.c_int64), ('d2h_bytes', ctypes.c_int64),
+                ('host_prepare_ms', ctypes.c_float), ('host_run_ms', ctypes.c_float),
+                ('host_fetch_ms', ctypes.c_float)]
 
 
 # every symbol include/tanw.h declares: (restype, argtypes)

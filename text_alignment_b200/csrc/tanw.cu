@@ -7,6 +7,7 @@
 #include "tanw_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -20,6 +21,14 @@ using namespace tanw;
 namespace {
 
 thread_local std::string g_last_error;   // for failures that have no context yet
+
+struct HostTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    float ms() const
+    {
+        return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
 
 struct DevBuf {
     void *p = nullptr;
@@ -47,6 +56,7 @@ struct tanw_ctx {
                 ev_d2h0 = nullptr, ev_d2h1 = nullptr;
     std::string err;
     int64_t arena_limit = 0;
+    int64_t total_mem = 0;
 
     DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_prog;
     std::vector<int> h_long;              // pairs routed to the chained-pass (whole-GPU) path
@@ -216,6 +226,7 @@ int tanw_create(int device, tanw_ctx **out)
     if (!ctx) return fail(nullptr, TANW_E_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->total_mem = (int64_t)prop.totalGlobalMem;
     memset(&ctx->timing, 0, sizeof ctx->timing);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -298,6 +309,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
                        const int32_t *m, int64_t n_pairs, const tanw_scoring *sc)
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    HostTimer host_timer;
     ctx->prepared = false;
     ctx->ran = false;
     if (n_pairs < 0 || symbols_len < 0) return fail(ctx, TANW_E_INVALID, "negative size");
@@ -389,11 +401,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     if (need_blocks < grid) grid = (int)std::max<int64_t>(need_blocks, 1);
     const int64_t slot_bytes = (max_slot + 255) / 256 * 256;
     int64_t limit = ctx->arena_limit;
-    if (limit == 0) {
-        size_t fr = 0, tot = 0;
-        TANW_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
-        limit = (int64_t)(tot / 10 * 4);
-    }
+    if (limit == 0) limit = ctx->total_mem / 10 * 4;     // no cudaMemGetInfo on the per-batch path
     if (max_long > (int64_t)(limit / 4 * 9))
         return fail(ctx, TANW_E_NOMEM, "a pair needs %lld bytes of traceback pointers; arena limit is %lld",
                     (long long)max_long, (long long)limit);
@@ -471,6 +479,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     ctx->timing.cells = cells;
     ctx->timing.ptr_bytes = ptr_total;
     ctx->timing.h2d_bytes = h2d;
+    ctx->timing.host_prepare_ms = host_timer.ms();
     ctx->prepared = true;
     return TANW_OK;
 }
@@ -479,6 +488,7 @@ int tanw_batch_run(tanw_ctx *ctx)
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     if (!ctx->prepared) return fail(ctx, TANW_E_STATE, "tanw_batch_run before tanw_batch_prepare");
+    HostTimer host_timer;
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     int launches = 0;
@@ -501,6 +511,7 @@ int tanw_batch_run(tanw_ctx *ctx)
     }
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
     ctx->timing.kernel_launches = launches;
+    ctx->timing.host_run_ms = host_timer.ms();
     ctx->ran = true;
     return TANW_OK;
 }
@@ -510,6 +521,7 @@ int tanw_batch_fetch(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     if (!ctx->ran) return fail(ctx, TANW_E_STATE, "tanw_batch_fetch before tanw_batch_run");
+    HostTimer host_timer;
     const int64_t P = ctx->n_pairs;
     if (P > 0 && (!ops_off || !ops_len)) return fail(ctx, TANW_E_INVALID, "NULL output table");
     if (ctx->ops_total > 0 && !ops) return fail(ctx, TANW_E_INVALID, "ops is NULL");
@@ -553,6 +565,7 @@ int tanw_batch_fetch(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_
     if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->timing.kernel_ms = ms;
     if (cudaEventElapsedTime(&ms, ctx->ev_d2h0, ctx->ev_d2h1) == cudaSuccess) ctx->timing.d2h_ms = ms;
     cudaGetLastError();
+    ctx->timing.host_fetch_ms = host_timer.ms();
     return TANW_OK;
 }
 
