@@ -134,5 +134,83 @@ def main():
     json.dump(app, open(os.path.join(HERE, 'appendix_c.json'), 'w'), indent=1, sort_keys=True)
 
 
+# ---- 4. the consumer: reference process() driven with mocked Gamera / OCR ----
+
+class _Dim(object):
+    def __init__(self, c, r):
+        self.ncols, self.nrows = c, r
+
+
+class _Img(object):
+    dim = _Dim(3000, 4000)
+
+
+def run_reference_process(A, transcript, boxes, params=None):
+    """Unmodified alignToOCR.process with preprocessing / OCR patched out; angle 0."""
+    import tempfile
+    chars = [A.CharBox(c, ul, lr) for c, ul, lr in boxes]
+    A.preproc.preprocess_images = lambda raw: (_Img(), None, 0.0)
+    A.preproc.identify_text_lines = lambda image, eroded: ([], [100, 240, 380], None)
+    A.perform_ocr_with_ocropus = lambda *a, **k: chars
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        return A.process(_Img(), transcript, 'nomodel', seq_align_params=params, wkdir_name='wk')
+    finally:
+        os.chdir(cwd)
+
+
+def consumer_golden():
+    A = ref_loader.load_aligntoocr()
+    pages = []
+    specs = [(9000 + k, 120 + 15 * k, 150 + 22 * k, 2, 12, k % 2 == 1, None) for k in range(10)]
+    specs.append((9100, 260, 900, 50, 200, True, None))                  # St. Gall-like long insertions
+    specs.append((9101, 200, 250, 2, 10, False, [5, -4, -2, -7, 0, -5]))
+    specs.append((9102, 600, 750, 5, 40, True, None))
+    for seed, n, m, lo, hi, abbr, params in specs:
+        t, boxes = synth.make_page(seed, n, m, lo, hi, abbreviations=abbr)
+        syl_boxes, _, _, all_chars = run_reference_process(A, t, boxes, params)
+        pages.append(dict(seed=seed, transcript=t, params=params,
+                          boxes=[[c, list(ul), list(lr)] for c, ul, lr in boxes],
+                          expanded_ocr=''.join(x.char for x in all_chars),
+                          syl_boxes=[[b.char, [int(v) for v in b.ul], [int(v) for v in b.lr]] for b in syl_boxes]))
+        print('page', seed, len(t), len(boxes), len(syl_boxes))
+    # syllabifier vectors: the reference demo sentence + generated words
+    rng = random.Random(99)
+    words = ['euouae', 'cuius', 'eius', '', 'quaecumque', 'ejus', 'michi', 'antiphonum', 'assistens',
+             'alleluya', 'dixit', 'extra', 'exhibeamus', 'oeix', 'aeiou', 'ththa', 'strophe']
+    for _ in range(400):
+        w = ''.join(rng.choice(synth.SYL) for _ in range(rng.randint(1, 4)))
+        words.append(w)
+    for _ in range(200):
+        w = ''.join(rng.choice('aeiouybcdfghlmnpqrstvx') for _ in range(rng.randint(1, 8)))
+        if any(v in w for v in 'aeiouy'):
+            words.append(w)
+    # a word whose vowels are all swallowed by consonant clusters ('quqs') never terminates in
+    # the reference (latinSyllabification.py:71): record null for those
+    import signal
+
+    class _Hang(Exception):
+        pass
+
+    def _alarm(signum, frame):
+        raise _Hang()
+    signal.signal(signal.SIGALRM, _alarm)
+    syl = []
+    for w in words:
+        signal.setitimer(signal.ITIMER_REAL, 0.5)
+        try:
+            syl.append([w, A.latsyl.syllabify_word(w)])
+        except _Hang:
+            syl.append([w, None])
+        finally:
+            signal.setitimer(signal.ITIMER_REAL, 0)
+    json.dump(dict(pages=pages, syllables=syl), open(os.path.join(HERE, 'consumer.json'), 'w'), indent=0)
+
+
 if __name__ == '__main__':
-    main()
+    if '--only-consumer' in sys.argv:
+        consumer_golden()
+    else:
+        main()
+        consumer_golden()

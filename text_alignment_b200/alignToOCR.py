@@ -1,0 +1,143 @@
+# -*- coding: utf-8 -*-
+"""The consumer of the alignment: OCR character boxes + transcript -> syllable boxes.
+
+Mirrors the part of the reference's ``alignToOCR.process`` that surrounds the hot path
+(/root/reference/alignToOCR.py:247-324): abbreviation expansion on the OCR boxes, the call of
+``textSeqCompare.perform_alignment`` (:273-276), gap insertion and its length invariant
+(:285-292), and the per-syllable regex + box union (:297-324).  ``CharBox`` (:35-58) and
+``to_JSON_dict`` (:333-351) keep their reference shape.  Image preprocessing, OCRopus and the
+rotation back into raw-image coordinates (:216-245, :327-328) are Gamera / subprocess work and
+stay out of scope: this module starts from the list of OCR character boxes.
+
+Host-side glue, not a kernel; the alignment it
+calls is the CUDA path.  ``boxes_for_pages`` aligns many pages in one launch.
+"""
+import re
+
+import numpy as np
+
+from . import latinSyllabification as latsyl
+from . import textSeqCompare as tsc
+
+
+class CharBox(object):
+    """A character (or syllable) with its bounding box; ``ul``/``lr`` None marks a gap
+    (alignToOCR.py:35-58)."""
+    __slots__ = ['char', 'ul', 'lr', 'ulx', 'lrx', 'uly', 'lry', 'width', 'height']
+
+    def __init__(self, char, ul=None, lr=None):
+        self.char = char
+        if (ul is None) or (lr is None):
+            self.ul = None
+            self.lr = None
+            return
+        self.ul = tuple(ul)
+        self.lr = tuple(lr)
+        self.ulx, self.uly = ul[0], ul[1]
+        self.lrx, self.lry = lr[0], lr[1]
+        self.width = lr[0] - ul[0]
+        self.height = lr[1] - ul[1]
+
+    def __repr__(self):
+        if self.ul and self.lr:
+            return '{}: {}, {}'.format(self.char, self.ul, self.lr)
+        return '{}: empty'.format(self.char)
+
+    def __eq__(self, other):
+        return (isinstance(other, CharBox) and self.char == other.char and
+                self.ul == other.ul and self.lr == other.lr)
+
+    __hash__ = None
+
+
+def expand_abbreviations(all_chars, abbreviations=None):
+    """alignToOCR.py:251-264.  For every abbreviation (dict order), while it occurs in the OCR
+    string, replace its boxes: segment i of the expansion inherits the box of the i-th
+    abbreviation character, one CharBox per expanded letter."""
+    abbreviations = latsyl.abbreviations if abbreviations is None else abbreviations
+    all_chars = list(all_chars)
+    for abb, segments in abbreviations.items():
+        while True:
+            ocr_str = ''.join(str(x.char) for x in all_chars)
+            idx = ocr_str.find(abb)
+            if idx == -1:
+                break
+            ins = []
+            for i, segment in enumerate(segments):
+                src = all_chars[i + idx]
+                ins += [CharBox(x, src.ul, src.lr) for x in segment]
+            all_chars = all_chars[:idx] + ins + all_chars[idx + len(abb):]
+    return all_chars
+
+
+def insert_gaps(all_chars, ocr_align):
+    """alignToOCR.py:285-292: a box-less CharBox('_') wherever the aligned OCR string has a
+    gap, so that the box list is index-aligned with ``tra_align``.  One O(L) pass instead of
+    the reference's repeated list.insert; the result (and the assertion) are the same."""
+    n_gaps = sum(1 for c in ocr_align if c == '_')
+    assert len(all_chars) + n_gaps == len(ocr_align), 'all_chars not same length as alignment: ' \
+        '{} vs {}'.format(len(all_chars) + n_gaps, len(ocr_align))
+    it = iter(all_chars)
+    return [CharBox('_') if c == '_' else next(it) for c in ocr_align]
+
+
+def syllable_boxes(transcript, tra_align, aligned_chars):
+    """alignToOCR.py:277, :297-324: for every syllable of the transcript find, from a moving
+    offset, the stretch of ``tra_align`` that spells it with optional gaps in between, and
+    union the boxes of the OCR characters aligned to that stretch."""
+    syls = latsyl.syllabify_text(transcript)
+    current_offset = 0
+    syl_boxes = []
+    for syl in syls:
+        if len(syl) < 1:
+            continue
+        elif len(syl) == 1:
+            syl_regex = syl
+        else:
+            syl_regex = syl[0] + syl[1:-1].replace('', '_*') + syl[-1]      # unescaped, as :304
+        syl_match = re.search(syl_regex, tra_align[current_offset:])
+        start = syl_match.start() + current_offset
+        end = syl_match.end() + current_offset
+        current_offset = end
+        align_boxes = [x for x in aligned_chars[start:end] if x.lr is not None]
+        if not align_boxes:                      # aligned to nothing in the OCR (:313)
+            continue
+        if len(set([x.uly for x in align_boxes])) > 1:        # spans text lines: keep the lower (:318-320)
+            lower_level = max(x.uly for x in align_boxes)
+            align_boxes = [b for b in align_boxes if b.uly == lower_level]
+        new_ul = (min(x.ulx for x in align_boxes), min(x.uly for x in align_boxes))
+        new_lr = (max(x.lrx for x in align_boxes), max(x.lry for x in align_boxes))
+        syl_boxes.append(CharBox(syl, new_ul, new_lr))
+    return syl_boxes
+
+
+def boxes_for_page(transcript, all_chars, seq_align_params=None, device=0):
+    """One page: what ``process`` does between OCR and un-rotation (alignToOCR.py:247-324).
+    Returns (syl_boxes, all_chars_after_expansion, tra_align, ocr_align)."""
+    return boxes_for_pages([(transcript, all_chars)], seq_align_params, devices=[device])[0]
+
+
+def boxes_for_pages(pages, seq_align_params=None, devices=None):
+    """Many pages, one alignment launch per device."""
+    expanded = [expand_abbreviations(chars) for _, chars in pages]
+    pairs = [(list(transcript), list(''.join(x.char for x in chars)))          # :267, :273
+             for (transcript, _), chars in zip(pages, expanded)]
+    aligned = tsc.perform_alignment_batch(pairs, scoring_system=seq_align_params, devices=devices)
+    out = []
+    for (transcript, _), chars, (tra, ocr) in zip(pages, expanded, aligned):
+        tra_align = ''.join(tra)                                               # :275-276
+        ocr_align = ''.join(ocr)
+        aligned_chars = insert_gaps(chars, ocr_align)
+        out.append((syllable_boxes(transcript, tra_align, aligned_chars), chars, tra_align, ocr_align))
+    return out
+
+
+def to_JSON_dict(syl_boxes, lines_peak_locs):
+    """alignToOCR.py:333-351."""
+    med_line_spacing = np.quantile(np.diff(lines_peak_locs), 0.75)
+    data = {'median_line_spacing': med_line_spacing, 'syl_boxes': []}
+    for s in syl_boxes:
+        data['syl_boxes'].append({'syl': s.char,
+                                  'ul': [int(s.ul[0]), int(s.ul[1])],
+                                  'lr': [int(s.lr[0]), int(s.lr[1])]})
+    return data

@@ -140,3 +140,40 @@ def bulk_pairs_numpy(seed, count, n_lo, n_hi, m_of_n, sub=0.20, indel=0.05):
         t_off[k] = pos; buf[pos:pos + n] = t; pos += n
         o_off[k] = pos; buf[pos:pos + m] = o; pos += m
     return buf, t_off, ns.astype(np.int64), o_off, ms
+
+
+# ---- synthetic OCR character boxes for the consumer ------------------------------
+
+def gen_char_boxes(rng, ocr, line_lo=40, line_hi=60, w_lo=10, w_hi=30, x0=100, y0=200, pitch=140, height=60):
+    """(char, ul, lr) per OCR character: lines of 40-60 chars, widths U[10,30] px, fixed pitch."""
+    boxes = []
+    x, y, left = x0, y0, rng.randint(line_lo, line_hi)
+    for c in ocr:
+        w = rng.randint(w_lo, w_hi)
+        boxes.append((c, (x, y), (x + w, y + height)))
+        x += w
+        left -= 1
+        if left == 0:
+            x, y, left = x0, y + pitch, rng.randint(line_lo, line_hi)
+    return boxes
+
+
+def drop_vowelless_tail(t):
+    """Truncation can leave a last word fragment without a vowel, which the reference's
+    syllabifier cannot handle (latinSyllabification.py:71); drop it (SURVEY App. C note)."""
+    words = t.split(' ')
+    while words and not any(v in words[-1] for v in 'aeiouy'):
+        words.pop()
+    return ' '.join(words)
+
+
+def make_page(seed, n, m, run_lo=5, run_hi=40, abbreviations=False):
+    """Transcript + OCR character boxes of one synthetic page."""
+    rng = random.Random(seed)
+    t = drop_vowelless_tail(gen_transcript(rng, n))
+    o = gen_ocr(rng, t, 0.20, 0.05, m, run_lo, run_hi)
+    if abbreviations:
+        o = o.replace('dominus', 'dns', 2).replace('alleluia', 'alla', 1)
+        if 'um ' in o:
+            o = o.replace('um ', u'ū ', 1)
+    return t, gen_char_boxes(rng, o)
