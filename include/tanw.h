@@ -108,6 +108,10 @@ int  tanw_set_arena_limit(tanw_ctx *ctx, int64_t bytes);
  * (BASELINE config 5, 100k x 80k) uses the whole GPU.  Default 2^26.  Results are identical
  * on both paths; the threshold only moves work between them. */
 int  tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells);
+/* Pairs with m <= 128 and n <= 4096 are aligned four per warp by the line kernel (8 lanes per
+ * pair; BASELINE config 3).  enabled = 0 sends them through the page kernel instead (same
+ * results; used by the tests to compare the two paths).  Default: enabled. */
+int  tanw_set_line_kernel(tanw_ctx *ctx, int enabled);
 
 /* ---- one-call batch alignment: the entry the reference's call site maps to ------------------
  * Replaces N calls of textSeqCompare.perform_alignment (textSeqCompare.py:13) -- copies the

@@ -311,3 +311,50 @@ def test_c5_whole_manuscript_pair(tsc, oracle):
     corner scores against the C oracle (the Python reference would need 384 GB)."""
     t, o = synth.c5_pair()
     _check_packed_vs_oracle(tsc, oracle, [(t, o)], threads=1)
+
+
+# ---- short pairs: four-pairs-per-warp line kernel (BASELINE config 3) ----------------------------
+
+def test_line_kernel_boundaries_and_quads(tsc, oracle):
+    """Strip-width classes (m = 32/64/96/128 edges), the m = 128/129 and n = 4096/4097 hand-over
+    to the page kernel, quads padded with empty slots and mixed with cell-less pairs."""
+    rng = random.Random(8)
+    sizes = [(1, 1), (1, 128), (128, 1), (7, 32), (8, 33), (9, 64), (40, 65), (41, 96), (120, 97),
+             (119, 128), (118, 129), (4096, 5), (4097, 5), (300, 100), (2, 2), (0, 7), (7, 0), (0, 0)]
+    for count in (1, 2, 3, 5):            # incomplete quads
+        pairs = [synth.make_pair(40 + k, n, m, 1, 6) for k, (n, m) in enumerate(sizes[:count])]
+        _check_packed_vs_oracle(tsc, oracle, pairs)
+    pairs = [synth.make_pair(70 + k, n, m, 1, 6) if n and m else ('a' * n, 'b' * m) for k, (n, m) in enumerate(sizes)]
+    rng.shuffle(pairs)
+    _check_packed_vs_oracle(tsc, oracle, pairs)
+
+
+def test_line_kernel_matches_page_kernel(tsc, oracle):
+    from text_alignment_b200 import _native
+    pairs = [synth.c3_pair(50000 + k) for k in range(1500)]
+    buf, t_off, n, o_off, m = _pack(pairs)
+    a = tsc.align_packed(buf, t_off, n, o_off, m, DEFAULT)
+    ctx = _native.Context(0)
+    try:
+        ctx.set_line_kernel(False)
+        b = ctx.align_batch(buf, t_off, n, o_off, m, ctx.make_scoring(*DEFAULT))
+    finally:
+        ctx.close()
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    total = int(a[1][-1] + n[-1] + m[-1])
+    for k in range(len(pairs)):
+        assert np.array_equal(a[0][a[1][k]:a[1][k] + a[2][k]], b[0][b[1][k]:b[1][k] + b[2][k]])
+    assert total == int((n.astype(np.int64) + m).sum())
+
+
+def test_line_kernel_general_gap_extend_and_callable(tsc, oracle):
+    """The gap_extend_y != 0 and substitution-table instantiations of the line kernel."""
+    import scorers
+    pairs = [synth.c3_pair(60000 + k) for k in range(300)]
+    _check_packed_vs_oracle(tsc, oracle, pairs, (7, -3, -4, -9, -1, -2, -1))
+    _check_packed_vs_oracle(tsc, oracle, pairs, (5, -4, -2, -7, 0, -5, -3))
+    t, o = synth.make_pair(61000, 100, 120, 2, 6)
+    system = [scorers.SCORERS['confusable'], -4, -6, -1, -2]
+    got = tsc.perform_alignment(list(t), list(o), scoring_system=system, return_scores=True)
+    want = oracle.perform_alignment(list(t), list(o), system, full=True)
+    assert (got[0], got[1]) == (want[0], want[1]) and tuple(got[2]) == _end(want[2]['end'])

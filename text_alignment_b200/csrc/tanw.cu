@@ -58,7 +58,12 @@ struct tanw_ctx {
     int64_t arena_limit = 0;
     int64_t total_mem = 0;
 
-    DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_prog;
+    DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_prog, d_quads;
+    std::vector<int> h_line;              // pairs routed to the four-per-warp line kernel
+    std::vector<int4> h_quads;
+    LineArgs largs;
+    int line_grid = 0, occ_line = 0;
+    bool use_lines = true;
     std::vector<int> h_long;              // pairs routed to the chained-pass (whole-GPU) path
     int long_capacity = 0;                // resident warps for a cooperative launch
     int64_t long_cells = int64_t(1) << 26;   // pairs with n*m >= this use the chained-pass path
@@ -246,6 +251,8 @@ int tanw_create(int device, tanw_ctx **out)
     }
     if (ctx->occ_plain < 1) ctx->occ_plain = 1;
     if (ctx->occ_subst < 1) ctx->occ_subst = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_line, align_lines_kernel<true, false>, kWarpsPerBlock * 32, 0);
+    if (ctx->occ_line < 1) ctx->occ_line = 1;
     {
         int occ_long = 0, coop = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, align_long_kernel<true, false>, 32, 0);
@@ -263,7 +270,7 @@ int tanw_destroy(tanw_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_pairs, &ctx->d_order, &ctx->d_counter, &ctx->d_arena,
-                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst, &ctx->d_prog };
+                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst, &ctx->d_prog, &ctx->d_quads };
     for (auto b : bufs) b->release();
     cudaEvent_t evs[] = { ctx->ev_h2d0, ctx->ev_h2d1, ctx->ev_k0, ctx->ev_k1, ctx->ev_d2h0, ctx->ev_d2h1 };
     for (auto ev : evs)
@@ -286,6 +293,13 @@ int tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells)
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     if (cells < 1) return fail(ctx, TANW_E_INVALID, "long-pair threshold must be >= 1 cell");
     ctx->long_cells = cells;
+    return TANW_OK;
+}
+
+int tanw_set_line_kernel(tanw_ctx *ctx, int enabled)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    ctx->use_lines = enabled != 0;
     return TANW_OK;
 }
 
@@ -324,6 +338,8 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     ctx->h_pairs.resize((size_t)n_pairs);
     ctx->h_ops_off.resize((size_t)n_pairs);
     ctx->h_long.clear();
+    ctx->h_line.clear();
+    int64_t max_line_slot = 0;
     int64_t ops_total = 0, cells = 0, ptr_total = 0, max_nm = 0, max_slot = 0, max_long = 0, max_long_bnd = 0;
     int max_n = 0, max_long_pass = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
@@ -347,6 +363,10 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
             max_long = std::max(max_long, pb);
             max_long_bnd = std::max(max_long_bnd, (npass + 1) * (np + 4));
             max_long_pass = std::max<int>(max_long_pass, (int)npass);
+        } else if (ctx->use_lines && mp <= kLineMaxM && np <= kLineMaxN) {
+            // short pair: 8 lanes per pair, four pairs per warp
+            ctx->h_line.push_back((int)p);
+            max_line_slot = std::max<int64_t>(max_line_slot, line_ptr_bytes((int)np, (int)mp));
         } else {
             max_slot = std::max(max_slot, pb);
             max_n = std::max(max_n, (int)np);
@@ -366,12 +386,40 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     ctx->h_order.clear();
     ctx->h_order.reserve((size_t)n_pairs);
     {
-        size_t li = 0;
+        size_t li = 0, si = 0;
         for (int64_t p = 0; p < n_pairs; ++p) {
             if (li < ctx->h_long.size() && ctx->h_long[li] == (int)p) { ++li; continue; }
+            if (si < ctx->h_line.size() && ctx->h_line[si] == (int)p) { ++si; continue; }
             ctx->h_order.push_back((int)p);
         }
     }
+    // ---- quads for the line kernel: equal strip width, similar height --------------------------
+    ctx->h_quads.clear();
+    if (!ctx->h_line.empty()) {
+        // counting sort on (strip-width class, n) descending; pairs without cells sort last
+        const std::vector<PairDesc> &hp = ctx->h_pairs;
+        const int NK = 4 * (kLineMaxN + 1);
+        auto key_of = [&hp](int p) {
+            const PairDesc &d = hp[(size_t)p];
+            const bool act = d.n > 0 && d.m > 0;
+            const int cls = act ? line_c(d.m) / 4 - 1 : 0;
+            return cls * (kLineMaxN + 1) + (act ? d.n : 0);
+        };
+        std::vector<int> count((size_t)NK + 1, 0);
+        for (int p : ctx->h_line) ++count[(size_t)(NK - 1 - key_of(p)) + 1];
+        for (int b = 1; b <= NK; ++b) count[(size_t)b] += count[(size_t)b - 1];
+        std::vector<int> sorted(ctx->h_line.size());
+        for (int p : ctx->h_line) sorted[(size_t)count[(size_t)(NK - 1 - key_of(p))]++] = p;
+        size_t i = 0;
+        while (i < sorted.size()) {
+            const int cls = key_of(sorted[i]) / (kLineMaxN + 1);
+            int q[4] = { -1, -1, -1, -1 };
+            int c = 0;
+            while (c < 4 && i < sorted.size() && key_of(sorted[i]) / (kLineMaxN + 1) == cls) q[c++] = sorted[i++];
+            ctx->h_quads.push_back(make_int4(q[0], q[1], q[2], q[3]));
+        }
+    }
+    const int64_t n_quads = (int64_t)ctx->h_quads.size();
     const int64_t n_batch = (int64_t)ctx->h_order.size();
     if (n_batch > 1) {
         // Largest pairs first (greedy longest-processing-time) only needs an approximate order:
@@ -431,6 +479,12 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     }
     ctx->grid = grid;
     const int64_t slots = (int64_t)grid * kWarpsPerBlock;
+    int line_grid = ctx->sm_count * ctx->occ_line;
+    if ((n_quads + kWarpsPerBlock - 1) / kWarpsPerBlock < line_grid)
+        line_grid = (int)std::max<int64_t>((n_quads + kWarpsPerBlock - 1) / kWarpsPerBlock, 1);
+    const int64_t line_slot = (max_line_slot + 255) / 256 * 256;
+    ctx->line_grid = line_grid;
+    const int64_t line_arena = n_quads ? (int64_t)line_grid * kWarpsPerBlock * 4 * line_slot : 0;
     const int bnd_rows = max_n + 4;      // bnd[1..n] plus the prefetch overrun
 
     // ---- device buffers and uploads -------------------------------------------------------
@@ -438,7 +492,8 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         ctx->d_pairs.reserve(sizeof(PairDesc) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_order.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_counter.reserve(256) != cudaSuccess ||
-        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(slots * slot_bytes, max_long), 256)) != cudaSuccess ||
+        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(std::max(slots * slot_bytes, max_long), line_arena), 256)) != cudaSuccess ||
+        ctx->d_quads.reserve(sizeof(int4) * (size_t)std::max<int64_t>(n_quads, 1)) != cudaSuccess ||
         ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(slots * bnd_rows, max_long_bnd)) != cudaSuccess ||
         ctx->d_prog.reserve(sizeof(int) * (size_t)(max_long_pass + 2)) != cudaSuccess ||
         ctx->d_ops.reserve((size_t)ops_total + 64) != cudaSuccess ||
@@ -459,7 +514,10 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         if (n_batch > 0)
             TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, ctx->h_order.data(), sizeof(int) * (size_t)n_batch,
                                            cudaMemcpyHostToDevice, ctx->stream));
-        h2d += (int64_t)sizeof(PairDesc) * n_pairs + (int64_t)sizeof(int) * n_batch;
+        if (n_quads > 0)
+            TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_quads.p, ctx->h_quads.data(), sizeof(int4) * (size_t)n_quads,
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        h2d += (int64_t)sizeof(PairDesc) * n_pairs + (int64_t)sizeof(int) * n_batch + (int64_t)sizeof(int4) * n_quads;
     }
     if (ctx->use_subst) {
         const size_t kk = (size_t)sc->subst_k * (size_t)sc->subst_k;
@@ -489,6 +547,18 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     a.ops_len = (int *)ctx->d_len.p;
     a.scores = (int *)ctx->d_scores.p;
 
+    LineArgs &la = ctx->largs;
+    la.sym = a.sym;
+    la.pairs = a.pairs;
+    la.quads = (const int4 *)ctx->d_quads.p;
+    la.counter = (unsigned *)ctx->d_counter.p + 1;
+    la.n_quads = (int)n_quads;
+    la.ptr_arena = a.ptr_arena;
+    la.slot_bytes = line_slot;
+    la.ops = a.ops;
+    la.ops_len = a.ops_len;
+    la.scores = a.scores;
+
     ctx->n_pairs = n_pairs;
     ctx->ops_total = ops_total;
     memset(&ctx->timing, 0, sizeof ctx->timing);
@@ -508,8 +578,20 @@ int tanw_batch_run(tanw_ctx *ctx)
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     int launches = 0;
+    if (ctx->args.n_pairs > 0 || ctx->largs.n_quads > 0)
+        TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 2 * sizeof(unsigned), ctx->stream));
+    if (ctx->largs.n_quads > 0) {
+        const int threads = kWarpsPerBlock * 32;
+        if (ctx->use_subst)
+            align_lines_kernel<true, false><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp);
+        else if (ctx->kp.ey == 0)
+            align_lines_kernel<false, true><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp);
+        else
+            align_lines_kernel<false, false><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp);
+        TANW_CUDA(ctx, cudaGetLastError());
+        ++launches;
+    }
     if (ctx->args.n_pairs > 0) {
-        TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned), ctx->stream));
         // three instantiations: tabulated scorer; equality scorer; equality scorer with
         // gap_extend_y == 0 (the reference's default_sys), which drops one add per cell
         if (ctx->use_subst)
@@ -519,7 +601,7 @@ int tanw_batch_run(tanw_ctx *ctx)
         else
             align_pairs_kernel<false, false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
         TANW_CUDA(ctx, cudaGetLastError());
-        launches = 1;
+        ++launches;
     }
     for (int p : ctx->h_long) {
         int rc = run_long_pair(ctx, p, &launches);

@@ -501,6 +501,249 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
     }
 }
 
+// ---- short pairs: four pairs per warp (BASELINE config 3, 40-120 character lines) -------------
+// A 32-lane wavefront on an 80-column pair is mostly ramp.  Here a pair gets 8 lanes (one
+// group), C = 4..16 columns per lane (m <= 128, a single pass, column 0 synthesised in
+// registers), so the skew costs 7 steps instead of 31, and a warp works on a "quad" of four
+// pairs of the same strip width and similar height at once.  Same strip_row inner loop, same
+// pointer bytes ([step][group lane][C]); the traceback runs for the four pairs concurrently,
+// each group pulling 8-row x 2-strip tiles into shared memory.
+constexpr int kLineG = 8;
+constexpr int kLineMaxC = 16;
+constexpr int kLineMaxM = kLineG * kLineMaxC;      // 128 columns
+constexpr int kLineMaxN = 4096;                    // bounds the per-group pointer slot
+constexpr int kLineTile = 2 * kLineMaxC / 4 + 1;   // words per tile row (two strips + pad)
+
+__host__ __device__ inline int line_c(int m) { return m <= 0 ? 4 : ((m + 31) / 32) * 4; }
+__host__ __device__ inline long long line_ptr_bytes(int n, int m)
+{
+    return (n <= 0 || m <= 0) ? 0 : ((long long)n + 8) * kLineG * line_c(m);
+}
+
+struct LineArgs {
+    const uint8_t  *sym;
+    const PairDesc *pairs;
+    const int4     *quads;       // four pair indices (or -1) of equal strip width, similar n
+    unsigned       *counter;
+    int             n_quads;
+    uint8_t        *ptr_arena;   // slot_bytes per 8-lane group
+    long long       slot_bytes;
+    uint8_t        *ops;
+    int            *ops_len;
+    int            *scores;
+};
+
+struct LineState {
+    int q_out, y_out, q_prev, y_prev, tnext, xe, cx, bq;
+    const uint8_t *tp;
+    uint8_t *pst;
+};
+
+template <int C, bool GUARDED, bool SUBST, bool EYZ>
+__device__ __forceinline__ void line_step(Strip<C> &s, LineState &ls, const KParams &kp, int n, bool act,
+                                          int t, int gl, int fin_lane, int fin_k, int (&cap)[3])
+{
+    const int i = t - gl;
+    int q_in = __shfl_up_sync(kFull, ls.q_out, 1, kLineG);
+    int y_in = __shfl_up_sync(kFull, ls.y_out, 1, kLineG);
+    if (gl == 0) { q_in = ls.bq | kTagM; y_in = ls.bq; }        // column 0: M = Y = bg*i (:54-56)
+    const int dul_in = max(ls.q_prev, ls.y_prev);
+    const int tch = ls.tnext;
+    if (!GUARDED || (i >= 0 && i < n)) ls.tnext = (int)__ldg(ls.tp);
+    if (!GUARDED || (act && i >= 1 && i <= n)) {
+        unsigned pw[C / 4];
+        const int kfin = (GUARDED && i == n && gl == fin_lane) ? fin_k : -1;
+        strip_row<C, GUARDED, SUBST, EYZ>(s, kp, tch, ls.xe, ls.cx, q_in, y_in, dul_in,
+                                          ls.q_out, ls.y_out, pw, kfin, cap);
+        store_ptr_words<C>(ls.pst, pw);
+    }
+    ls.q_prev = q_in;
+    ls.y_prev = y_in;
+    ls.xe += kp.ex;
+    ls.cx -= kp.ex;
+    ls.bq += kp.bg;
+    ls.tp += 1;
+    ls.pst += kLineG * C;
+}
+
+// Traceback of the (up to) four pairs of a quad, one per 8-lane group, concurrently.
+template <int C>
+__device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m, bool act,
+                                                uint8_t *ops_end, unsigned *tile, int gl)
+{
+    int x = n, y = m, k = 0, st = -1;
+    while (__any_sync(kFull, act && x > 0 && y > 0)) {
+        const bool mine = act && x > 0 && y > 0;
+        const int sidx = mine ? (y - 1) / C : 0;             // strip that holds column y
+        const int row = x - gl;
+        unsigned w[2 * C / 4];
+#pragma unroll
+        for (int q = 0; q < 2 * C / 4; ++q) w[q] = 0;
+        if (mine && row >= 1) {
+            const unsigned *hi = reinterpret_cast<const unsigned *>(ptr + ((size_t)(row + sidx) * kLineG + sidx) * C);
+#pragma unroll
+            for (int q = 0; q < C / 4; ++q) w[C / 4 + q] = __ldcg(hi + q);
+            if (sidx >= 1) {
+                const unsigned *lo = reinterpret_cast<const unsigned *>(ptr + ((size_t)(row + sidx - 1) * kLineG + sidx - 1) * C);
+#pragma unroll
+                for (int q = 0; q < C / 4; ++q) w[q] = __ldcg(lo + q);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 2 * C / 4; ++q) tile[gl * kLineTile + q] = w[q];
+        __syncwarp();
+        if (mine && gl == 0) {
+            const int col0 = (sidx - 1) * C;                 // 0-based column of the window start
+            int r = 0;
+            while (r < kLineG && x > 0 && y > 0) {
+                const int cw = (y - 1) - col0;
+                if (cw < 0) break;
+                const unsigned b = (tile[r * kLineTile + (cw >> 2)] >> (8 * (cw & 3))) & 0xFFu;
+                if (st < 0) st = 2 - (int)(b & 3u);                                   // :102
+                int op;
+                if (st == 0)      { op = 0; st = 2 - (int)(b & 3u);        --x; --y; ++r; }   // :115-125
+                else if (st == 1) { op = 1; st = 2 - (int)((b >> 2) & 3u); --x; ++r; }        // :128-135
+                else              { op = 2; st = 2 - (int)((b >> 4) & 3u); --y; }             // :138-145
+                ++k;
+                *(ops_end - k) = (uint8_t)op;
+            }
+        }
+        x = __shfl_sync(kFull, x, 0, kLineG);
+        y = __shfl_sync(kFull, y, 0, kLineG);
+    }
+    if (gl == 0) {
+        while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // :154-158
+        while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // :160-164
+    }
+    return __shfl_sync(kFull, k, 0, kLineG);
+}
+
+template <int C, bool SUBST, bool EYZ>
+__device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, int p, uint8_t *ptr,
+                                          unsigned *tile, int lane)
+{
+    const int gl = lane & (kLineG - 1);
+    int n = 0, m = 0;
+    long long ops_off = 0;
+    const uint8_t *T = a.sym, *O = a.sym;
+    if (p >= 0) {
+        const PairDesc pd = a.pairs[p];
+        n = pd.n; m = pd.m; ops_off = pd.ops_off;
+        T = a.sym + pd.t_off; O = a.sym + pd.o_off;
+    }
+    const bool act = (n > 0 && m > 0);
+    if (!act) { T = a.sym; O = a.sym; }
+    // tallest / shortest active pair of the quad (n is uniform inside a group)
+    int nmax = act ? n : 0, nmin = act ? n : 0x7fffffff;
+#pragma unroll
+    for (int d = kLineG; d < 32; d <<= 1) {
+        nmax = max(nmax, __shfl_xor_sync(kFull, nmax, d));
+        nmin = min(nmin, __shfl_xor_sync(kFull, nmin, d));
+    }
+    int cap[3];
+    cap[0] = kp.bg * (n > 0 ? n : m);                        // corner scores without any cell (:53-60)
+    cap[1] = (n > 0) ? kNeg : kp.bg * m;
+    cap[2] = (n > 0) ? kp.bg * n : kNeg;
+    if (n == 0 && m == 0) { cap[0] = 0; cap[1] = 0; cap[2] = kNeg; }
+
+    if (nmax > 0) {
+        const int c0 = gl * C;
+        Strip<C> s;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int c = c0 + k;
+            s.oc[k] = (act && c < m) ? (int)__ldg(O + c) : (SUBST ? 0 : 0x100);
+            const int base = kp.bg * (c + 1);                // row 0 (:57-60)
+            s.W[k] = base | kTagM;
+            s.Xh[k] = base | kTagX;
+            s.D[k] = base | kTagM;
+        }
+        LineState ls;
+        ls.q_out = (kp.bg * (c0 + C)) | kTagM;
+        ls.y_out = kNeg;
+        ls.q_prev = (kp.bg * c0) | kTagM;
+        ls.y_prev = kNeg;
+        ls.tnext = (gl == 0) ? (int)__ldg(T) : 0;
+        ls.tp = T + (1 - gl);
+        ls.xe = kp.ex * (1 - gl);
+        ls.cx = kp.ox - ls.xe;
+        ls.bq = kp.bg * (1 - gl);
+        ls.pst = ptr + ((size_t)kLineG + gl) * C;            // step t = 1
+        const int fin_lane = act ? (m - 1) / C : -1;
+        const int fin_k = act ? (m - 1) % C : -1;
+        const int last_step = nmax + kLineG - 1;
+        int t = 1;
+        for (; t <= min(kLineG - 1, last_step); ++t)         // ramp-up
+            line_step<C, true, SUBST, EYZ>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
+        for (; t <= nmin - 1; ++t)                           // every lane of every group on a row in [1, n-1]
+            line_step<C, false, SUBST, EYZ>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
+        for (; t <= last_step; ++t)                          // ramp-down and the taller pairs' tails
+            line_step<C, true, SUBST, EYZ>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
+        {   // the lane of the group that owns column m holds the corner scores
+            const int src = (lane & ~(kLineG - 1)) + (act ? fin_lane : 0);
+            const int v0 = __shfl_sync(kFull, cap[0], src);
+            const int v1 = __shfl_sync(kFull, cap[1], src);
+            const int v2 = __shfl_sync(kFull, cap[2], src);
+            if (act) { cap[0] = v0; cap[1] = v1; cap[2] = v2; }
+        }
+    }
+    __syncwarp();
+    uint8_t *ops = a.ops + ops_off;
+    const int L = traceback_groups<C>(ptr, n, m, act, ops + (size_t)n + (size_t)m, tile, gl);
+    if (p >= 0 && gl == 0) {
+        a.ops_len[p] = L;
+        if (a.scores) {
+            a.scores[3 * (size_t)p + 0] = score_out(cap[0]);
+            a.scores[3 * (size_t)p + 1] = score_out(cap[1]);
+            a.scores[3 * (size_t)p + 2] = score_out(cap[2]);
+        }
+    }
+    // move each op string to the start of its buffer
+    const int shift = (p >= 0) ? n + m - L : 0;
+    int rounds = (shift > 0) ? (L + kLineG - 1) / kLineG : 0;
+#pragma unroll
+    for (int d = kLineG; d < 32; d <<= 1) rounds = max(rounds, __shfl_xor_sync(kFull, rounds, d));
+    for (int it = 0; it < rounds; ++it) {
+        const int q = it * kLineG + gl;
+        uint8_t v = 0;
+        const bool on = shift > 0 && q < L;
+        if (on) v = __ldcg(ops + shift + q);
+        __syncwarp();
+        if (on) ops[q] = v;
+        __syncwarp();
+    }
+}
+
+template <bool SUBST, bool EYZ>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
+align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
+{
+    __shared__ unsigned tiles[kWarpsPerBlock][4 * kLineG * kLineTile];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int g = lane >> 3;
+    const long long slot = ((long long)blockIdx.x * kWarpsPerBlock + warp) * 4 + g;
+    uint8_t *const ptr = a.ptr_arena + (size_t)slot * (size_t)a.slot_bytes;
+    unsigned *const tile = tiles[warp] + g * (kLineG * kLineTile);
+    for (;;) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(a.counter, 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if (idx >= (unsigned)a.n_quads) break;
+        const int4 quad = a.quads[idx];
+        const int p = (g == 0) ? quad.x : (g == 1) ? quad.y : (g == 2) ? quad.z : quad.w;
+        const int C = line_c(a.pairs[quad.x].m);             // uniform: a quad holds one strip width
+        switch (C) {
+        case 4:  line_quad<4,  SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
+        case 8:  line_quad<8,  SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
+        case 12: line_quad<12, SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
+        default: line_quad<16, SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- one huge pair: chained passes ---------------------------------------------------------------
 // BASELINE config 5 (100k x 80k): a single pair must use the whole GPU.  Every pass (a stripe
 // of 32*C columns) gets its own warp, all passes are resident at once (cooperative launch), and
