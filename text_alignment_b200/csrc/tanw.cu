@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -66,6 +67,8 @@ struct tanw_ctx {
     bool use_lines = true;
     std::vector<int> h_long;              // pairs routed to the chained-pass (whole-GPU) path
     int long_capacity = 0;                // resident warps for a cooperative launch
+    int long_epoch = 0;                   // stamps the chain records of a launch
+    DevBuf d_chain;
     int64_t long_cells = int64_t(1) << 26;   // pairs with n*m >= this use the chained-pass path
     std::vector<PairDesc> h_pairs;
     std::vector<int> h_order;
@@ -127,6 +130,34 @@ bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
     return (max_n_plus_m + 2) * pmax < (int64_t(1) << 25);
 }
 
+// The chain records carry an epoch stamp; fresh memory must not contain a live one.
+cudaError_t reserve_zeroed(tanw_ctx *ctx, DevBuf &buf, size_t bytes)
+{
+    if (bytes <= buf.cap) return cudaSuccess;
+    cudaError_t e = buf.reserve(bytes);
+    if (e == cudaSuccess && buf.cap) {
+        e = cudaMemsetAsync(buf.p, 0, buf.cap, ctx->stream);
+        ctx->long_epoch = 0;
+    }
+    return e;
+}
+
+// Stripe width of a chained-pass pair.  A stripe is one warp that is bound by its own
+// instruction latency, so more, narrower stripes mean more warps per SM sub-partition; but every
+// stripe also adds ~46 steps of pipeline fill (31 rows of lane skew + the boundary look-ahead).
+// Measured on config 5 (100k columns): C = 4 / 8 / 12 / 16 -> 37.0 / 35.5 / 37.3 / 39.9 ms.
+int long_stripe_c(const tanw_ctx *ctx, int m)
+{
+    if (const char *e = getenv("TANW_LONG_C")) {          // tuning experiments only
+        const int c = atoi(e);
+        if (c >= 4 && c <= kMaxC && c % 4 == 0 && (m + 32 * c - 1) / (32 * c) <= ctx->long_capacity) return c;
+    }
+    if ((m + 255) / 256 >= 2 * ctx->sm_count && (m + 255) / 256 <= ctx->long_capacity) return 8;
+    for (int c = 4; c < kMaxC; c += 4)
+        if ((m + 32 * c - 1) / (32 * c) <= ctx->long_capacity) return c;
+    return kMaxC;
+}
+
 // One whole-manuscript pair on the chained-pass path: init, one cooperative launch per wave
 // of resident stripes, traceback.
 int run_long_pair(tanw_ctx *ctx, int p, int *launches)
@@ -138,15 +169,14 @@ int run_long_pair(tanw_ctx *ctx, int p, int *launches)
     la.n = pd.n;
     la.m = pd.m;
     la.ptr = (uint8_t *)ctx->d_arena.p;
-    la.bnd = (int2 *)ctx->d_bnd.p;
-    la.bnd_stride = (long long)pd.n + 4;
-    la.prog = (int *)ctx->d_prog.p;
+    la.chain = (int4 *)ctx->d_chain.p;
+    la.chain_stride = (long long)pd.n + 4;
+    la.epoch = ++ctx->long_epoch;
+    if (la.epoch == 0) la.epoch = ++ctx->long_epoch;
     la.pass0 = 0;
+    la.cfull = long_stripe_c(ctx, pd.m);
     la.scores = (int *)ctx->d_scores.p + 3 * (size_t)p;
-    const int npass = (pd.m + kPassW - 1) / kPassW;
-    long_init_kernel<<<std::min(64, (pd.n + 255) / 256 + 1), 256, 0, ctx->stream>>>(la, ctx->kp);
-    TANW_CUDA(ctx, cudaGetLastError());
-    ++*launches;
+    const int npass = (pd.m + 32 * la.cfull - 1) / (32 * la.cfull);
     for (int w0 = 0; w0 < npass; w0 += ctx->long_capacity) {
         la.pass0 = w0;
         const int grid = std::min(ctx->long_capacity, npass - w0);
@@ -157,7 +187,7 @@ int run_long_pair(tanw_ctx *ctx, int p, int *launches)
         TANW_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(32), args, 0, ctx->stream));
         ++*launches;
     }
-    trace_long_kernel<<<1, 32, 0, ctx->stream>>>(la.ptr, pd.n, pd.m, (uint8_t *)ctx->d_ops.p + pd.ops_off,
+    trace_long_kernel<<<1, 32, 0, ctx->stream>>>(la.ptr, pd.n, pd.m, la.cfull, (uint8_t *)ctx->d_ops.p + pd.ops_off,
                                                  (int *)ctx->d_len.p + p);
     TANW_CUDA(ctx, cudaGetLastError());
     ++*launches;
@@ -270,7 +300,7 @@ int tanw_destroy(tanw_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_pairs, &ctx->d_order, &ctx->d_counter, &ctx->d_arena,
-                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst, &ctx->d_prog, &ctx->d_quads };
+                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst, &ctx->d_prog, &ctx->d_quads, &ctx->d_chain };
     for (auto b : bufs) b->release();
     cudaEvent_t evs[] = { ctx->ev_h2d0, ctx->ev_h2d1, ctx->ev_k0, ctx->ev_k1, ctx->ev_d2h0, ctx->ev_d2h1 };
     for (auto ev : evs)
@@ -359,8 +389,9 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         if (np * mp >= ctx->long_cells && ctx->long_capacity > 0) {
             // whole-manuscript pair: one warp per column stripe, all stripes resident at once
             ctx->h_long.push_back((int)p);
-            const int64_t npass = (mp + kPassW - 1) / kPassW;
-            max_long = std::max(max_long, pb);
+            const int cf = long_stripe_c(ctx, (int)mp);
+            const int64_t npass = (mp + 32 * cf - 1) / (32 * cf);
+            max_long = std::max<int64_t>(max_long, ptr_bytes((int)np, (int)mp, cf));
             max_long_bnd = std::max(max_long_bnd, (npass + 1) * (np + 4));
             max_long_pass = std::max<int>(max_long_pass, (int)npass);
         } else if (ctx->use_lines && mp <= kLineMaxM && np <= kLineMaxN) {
@@ -494,8 +525,8 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         ctx->d_counter.reserve(256) != cudaSuccess ||
         ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(std::max(slots * slot_bytes, max_long), line_arena), 256)) != cudaSuccess ||
         ctx->d_quads.reserve(sizeof(int4) * (size_t)std::max<int64_t>(n_quads, 1)) != cudaSuccess ||
-        ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(slots * bnd_rows, max_long_bnd)) != cudaSuccess ||
-        ctx->d_prog.reserve(sizeof(int) * (size_t)(max_long_pass + 2)) != cudaSuccess ||
+        ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(slots * bnd_rows, 1)) != cudaSuccess ||
+        reserve_zeroed(ctx, ctx->d_chain, sizeof(int4) * (size_t)max_long_bnd) != cudaSuccess ||
         ctx->d_ops.reserve((size_t)ops_total + 64) != cudaSuccess ||
         ctx->d_len.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_scores.reserve(sizeof(int) * 3 * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess) {

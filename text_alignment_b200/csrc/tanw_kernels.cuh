@@ -45,7 +45,6 @@ constexpr int      kMaxC    = TANW_MAXC;         // widest strip (columns per la
 constexpr int      kPassW   = 32 * kMaxC;        // columns of a full pass
 constexpr int      kWarpsPerBlock = 4;
 constexpr unsigned kFull    = 0xFFFFFFFFu;
-constexpr int      kTileStride = 9;              // words per tile row in shared memory (8 + pad)
 
 struct KParams {
     int maT, miT;            // (match<<2)|kTagM, (mismatch<<2)|kTagM
@@ -80,12 +79,12 @@ struct BatchArgs {
 __host__ __device__ inline int remainder_c(int r) { return ((r + 127) / 128) * 4; }
 
 // Bytes of traceback pointers of one pair (all passes, (n+32) step slots each).
-__host__ __device__ inline long long ptr_bytes(int n, int m)
+__host__ __device__ inline long long ptr_bytes(int n, int m, int cfull = kMaxC)
 {
     if (n <= 0 || m <= 0) return 0;
     long long steps = (long long)n + 32;
-    int nfull = m / kPassW, r = m % kPassW;
-    return steps * 32 * ((long long)nfull * kMaxC + (r ? remainder_c(r) : 0));
+    int nfull = m / (32 * cfull), r = m % (32 * cfull);
+    return steps * 32 * ((long long)nfull * cfull + (r ? remainder_c(r) : 0));
 }
 
 // Bitwise cleaning of the tag bits as opaque asm: the pointer extraction below computes
@@ -192,40 +191,78 @@ struct PassState {
     const int2 *bp;        // &bnd[t+2]: next boundary row to prefetch
     int2 *bw;              // &bnd[i+1]: where lane 31 leaves its right edge next
     uint8_t *pst;          // pointer bytes of this lane for the next step
-    int avail;             // chained passes: rows of the left boundary known to be published
+    int2 blk_cur, blk_next; // chained passes: 8-row blocks of the left boundary, one row per lane 0..7
 };
 
-// Chained passes (one huge pair spread over many warps): pass w publishes how many rows of its
-// right edge are visible in prog_out; pass w+1 polls it before prefetching a boundary row.
-__device__ __forceinline__ int ld_acquire(const int *p)
+// Chained passes (one huge pair spread over many warps): stripe w leaves its right edge in
+// global memory for stripe w+1.  No fences and no progress counters: every row is one 16-byte
+// record (Q, epoch, Y, epoch); a record is valid once both halves carry the epoch of the
+// current launch (8-byte stores are single transactions, so a torn record shows a stale flag
+// in one half and is simply polled again).  Measured: a __threadfence + st.release per 8 rows
+// cost more than the stripe's arithmetic.
+struct Chain {
+    const int4 *in;        // records of the stripe to the left, indexed by row (unused if first)
+    int4 *out;             // records this stripe produces
+    int epoch;             // nonzero, unique per launch
+    bool first;            // stripe 0: the left boundary is column 0 of the matrices
+};
+constexpr int kChainBlock = 8;         // boundary rows fetched per coalesced load (lanes 0..7)
+
+__device__ __forceinline__ int4 ld_volatile_v4(const int4 *p)
 {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    int4 v;
+    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v)
+__device__ __forceinline__ void st_volatile_v4(int4 *p, int4 v)
 {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+    asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-constexpr int kPublishEvery = 32;      // rows between two progress publications
+// Rows base .. base+7 of the left stripe's edge, one per lane 0..7 (spins until they are there).
+__device__ __forceinline__ int2 chain_fetch(const Chain &ch, int base, int n, int lane)
+{
+    int4 v = make_int4(0, ch.epoch, 0, ch.epoch);
+    const bool mine = lane < kChainBlock && base + lane <= n;
+    for (;;) {
+        if (mine) v = ld_volatile_v4(ch.in + base + lane);
+        if (__all_sync(kFull, v.y == ch.epoch && v.w == ch.epoch)) break;
+    }
+    return make_int2(v.x, v.z);
+}
 
 // One wavefront step of one pass.  GUARDED steps check whether the lane's row is inside
 // [1, n] (ramp-up / ramp-down) and capture the corner scores; steady steps do neither.
 template <int C, bool GUARDED, bool SUBST, bool EYZ, bool CHAINED>
 __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KParams &kp,
                                           int n, int t, int lane, bool has_next,
-                                          int fin_lane, int fin_k, int (&cap)[3],
-                                          const int *prog_in, int *prog_out)
+                                          int fin_lane, int fin_k, int (&cap)[3], const Chain &ch)
 {
     const int i = t - lane;                       // this lane's row in this step
     int q_in = __shfl_up_sync(kFull, ps.q_out, 1);
     int y_in = __shfl_up_sync(kFull, ps.y_out, 1);
     if (lane == 0) { q_in = ps.bnext.x; y_in = ps.bnext.y; }
     if (!GUARDED || t + 1 <= n) {
-        if (CHAINED) {                            // warp-uniform spin on the producer's progress
-            while (ps.avail < t + 1) ps.avail = ld_acquire(prog_in);
+        if (CHAINED) {
+            // A chained stripe has an SM sub-partition almost to itself, so a load issued one
+            // step ahead does not hide L2 latency.  The boundary arrives in blocks of 8 rows
+            // (one coalesced load per block, fetched a block ahead) and reaches lane 0 by shuffle.
+            const int r = t + 1;                          // boundary row needed by the next step
+            if (ch.first) {
+                ps.bnext = make_int2((kp.bg * r) | kTagM, kp.bg * r);       // column 0 (:54-56)
+            } else {
+                const int j = (r - 1) & (kChainBlock - 1);
+                if (j == 0) {
+                    ps.blk_cur = ps.blk_next;
+                    if (r + kChainBlock <= n) ps.blk_next = chain_fetch(ch, r + kChainBlock, n, lane);
+                }
+                ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, j);
+                ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, j);
+            }
+        } else {
+            ps.bnext = __ldcg(ps.bp);             // same address in every lane
         }
-        ps.bnext = __ldcg(ps.bp);                 // same address in every lane
     }
     const int dul_in = max(ps.q_prev, ps.y_prev); // D of (i-1, left neighbour column)
     const int tch = ps.tnext;
@@ -237,11 +274,8 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
                                           ps.q_out, ps.y_out, pw, kfin, cap);
         store_ptr_words<C>(ps.pst, pw);
         if (has_next && lane == 31) {
-            __stcg(ps.bw, make_int2(ps.q_out, ps.y_out));
-            if (CHAINED && ((i & (kPublishEvery - 1)) == 0 || i == n)) {
-                __threadfence();
-                st_release(prog_out, i);
-            }
+            if (CHAINED) st_volatile_v4(ch.out + i, make_int4(ps.q_out, ch.epoch, ps.y_out, ch.epoch));
+            else         __stcg(ps.bw, make_int2(ps.q_out, ps.y_out));
         }
     }
     ps.q_prev = q_in;
@@ -266,7 +300,7 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
                                           const uint8_t *__restrict__ O, int n, int m, int j0,
                                           bool has_next, const int2 *bnd, int2 *bnd_out,
                                           uint8_t *__restrict__ ptr, int fin_lane, int fin_k,
-                                          int (&cap)[3], const int *prog_in, int *prog_out)
+                                          int (&cap)[3], const Chain &ch)
 {
     const int lane = threadIdx.x & 31;
     const int c0 = j0 + lane * C;                 // 0-based first column of the strip
@@ -287,11 +321,20 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     ps.y_out = kNeg;
     ps.q_prev = (kp.bg * c0) | kTagM;             // left neighbour column, row 0
     ps.y_prev = kNeg;                             // (Y[0][j] = -inf, also at j = 0)
-    ps.avail = 0;
+    ps.blk_cur = make_int2(0, 0);
+    ps.blk_next = make_int2(0, 0);
     if (CHAINED) {
-        while (ps.avail < 1) ps.avail = ld_acquire(prog_in);
+        if (ch.first) {
+            ps.bnext = make_int2(kp.bg | kTagM, kp.bg);                     // row 1 of column 0
+        } else {
+            ps.blk_cur = chain_fetch(ch, 1, n, lane);                       // rows 1..8
+            if (1 + kChainBlock <= n) ps.blk_next = chain_fetch(ch, 1 + kChainBlock, n, lane);
+            ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, 0);
+            ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, 0);
+        }
+    } else {
+        ps.bnext = __ldcg(bnd + 1);
     }
-    ps.bnext = __ldcg(bnd + 1);
     ps.bp = bnd + 2;
     ps.bw = bnd_out + (1 - lane);
     ps.tnext = (lane == 0) ? (int)__ldg(T) : 0;
@@ -304,11 +347,11 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     const int ramp_end = min(31, last_step);
     int t = 1;
     for (; t <= ramp_end; ++t)                    // ramp-up: lanes join one per step
-        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, prog_in, prog_out);
+        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
     for (; t <= n - 1; ++t)                       // steady state: every lane on a row in [1, n-1]
-        pass_step<C, false, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, prog_in, prog_out);
+        pass_step<C, false, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
     for (; t <= last_step; ++t)                   // ramp-down: last row, lanes leave one per step
-        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, prog_in, prog_out);
+        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
 }
 
 template <bool SUBST, bool EYZ, bool CHAINED>
@@ -316,13 +359,13 @@ __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const ui
                                               const uint8_t *O, int n, int m, int j0,
                                               bool has_next, const int2 *bnd, int2 *bnd_out,
                                               uint8_t *ptr, int fin_lane, int fin_k, int (&cap)[3],
-                                              const int *prog_in, int *prog_out)
+                                              const Chain &ch)
 {
 #define TANW_CASE(CC)                                                                              \
     case CC:                                                                                       \
         if constexpr (CC <= kMaxC)                                                                 \
             fill_pass<CC, SUBST, EYZ, CHAINED>(kp, T, O, n, m, j0, has_next, bnd, bnd_out, ptr,     \
-                                               fin_lane, fin_k, cap, prog_in, prog_out);            \
+                                               fin_lane, fin_k, cap, ch);                           \
         break;
     switch (C) {
         TANW_CASE(4) TANW_CASE(8) TANW_CASE(12) TANW_CASE(16)
@@ -331,74 +374,112 @@ __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const ui
 #undef TANW_CASE
 }
 
-// Address of the pointer byte of cell (i, j), 1-based, inside a pair's pointer block.
+// Where the pointer bytes of a pair live: passes of 32*cfull columns (the last one narrower),
+// each laid out [step t][lane][C].  cfull is kMaxC for the batched kernel and the stripe width
+// chosen by the host for a chained-pass (whole-manuscript) pair.
 struct PtrMap {
     long long steps;     // n + 32
-    int nfull, cr;       // full passes, strip width of the remainder pass
-    __device__ __forceinline__ PtrMap(int n, int m)
+    int cfull, passw;    // strip width and columns of a full pass
+    int nfull, cr;       // number of full passes, strip width of the remainder pass
+    __device__ __forceinline__ PtrMap(int n, int m, int cfull_)
     {
         steps = (long long)n + 32;
-        nfull = m / kPassW;
-        const int r = m % kPassW;
+        cfull = cfull_;
+        passw = 32 * cfull_;
+        nfull = m / passw;
+        const int r = m % passw;
         cr = r ? remainder_c(r) : 0;
-    }
-    __device__ __forceinline__ long long offset(int i, int j) const
-    {
-        const int c = j - 1;
-        int p = c / kPassW;
-        int C = kMaxC;
-        if (p >= nfull) { p = nfull; C = cr; }
-        const int cc = c - p * kPassW;
-        const int lane = cc / C, k = cc - lane * C;
-        const long long base = (long long)p * steps * kPassW;
-        return base + ((long long)(i + lane) * 32 + lane) * C + k;
     }
 };
 
+// Cursor over the pointer words (4 cells each) of one matrix row, moving towards column 1.
+struct PtrCursor {
+    long long rowless;   // offset of the word for row 0 (add row * 32 * C)
+    int p, ls, k4, C;    // pass, lane of the strip, word inside the strip, strip width
+    __device__ __forceinline__ void seek(const PtrMap &map, int word_col)     // word_col = (j-1) >> 2
+    {
+        const int c = word_col * 4;
+        p = c / map.passw;
+        C = map.cfull;
+        if (p >= map.nfull) { p = map.nfull; C = map.cr; }
+        const int cc = c - p * map.passw;
+        ls = cc / C;
+        k4 = (cc - ls * C) >> 2;
+        rebase(map);
+    }
+    __device__ __forceinline__ void rebase(const PtrMap &map)
+    {
+        rowless = (long long)p * map.steps * map.passw + (long long)ls * 33 * C + 4 * k4;
+    }
+    __device__ __forceinline__ long long at_row(int row) const { return rowless + (long long)row * 32 * C; }
+    __device__ __forceinline__ void left(const PtrMap &map)                    // one word towards column 1
+    {
+        if (k4 > 0) { --k4; rowless -= 4; return; }
+        if (ls > 0) { --ls; }
+        else { --p; C = map.cfull; ls = 31; }      // only ever called while word_col > 0
+        k4 = C / 4 - 1;
+        rebase(map);
+    }
+};
+
+constexpr int kTileRows = 64;                      // rows of a traceback tile (two per lane)
+constexpr int kTileWords = 16;                     // 64 columns of a traceback tile
+constexpr int kTileStride = kTileWords + 1;        // words per tile row in shared memory (+ pad)
+
 // Traceback of one pair (textSeqCompare.py:96-164) by one warp.  The pointer chase is a chain
-// of dependent loads, so the warp first pulls the 32x32 tile of pointer bytes whose bottom-
-// right corner is the current cell into shared memory (lane r: row x-r, 32 independent loads),
-// then lane 0 walks inside the tile.  Ops are written back to front at the END of the pair's
-// op buffer (capacity n+m); returns the number of columns (valid in every lane).
-__device__ __forceinline__ int traceback_warp(const uint8_t *ptr, int n, int m, uint8_t *ops_end,
-                                              unsigned *tile, int lane)
+// of dependent loads, so the warp first pulls the 64-row x 64-column tile of pointer bytes
+// whose bottom-right corner is the current cell into shared memory (lane r: rows x-r and
+// x-32-r, 32 independent word loads), then lane 0 walks inside the tile.  Ops are written back
+// to front at the END of the pair's op buffer (capacity n+m); returns the number of columns
+// (valid in every lane).
+__device__ __forceinline__ int traceback_warp(const uint8_t *ptr, int n, int m, int cfull,
+                                              uint8_t *ops_end, unsigned *tile, int lane)
 {
     int x = n, y = m, k = 0;
     if (n > 0 && m > 0) {
-        const PtrMap map(n, m);
+        const PtrMap map(n, m, cfull);
         int st = -1;                                       // -1: take mat_ptr[n][m] first (:102)
         while (x > 0 && y > 0) {
-            // ---- tile load: rows x-lane, columns y-31 .. y ---------------------------------
-            const int row = x - lane;
-            unsigned words[8];
+            // ---- tile load: word columns wq_hi-15 .. wq_hi, rows x-lane and x-32-lane ------
+            const int wq_hi = (y - 1) >> 2;
+            const int row0 = x - lane, row1 = x - 32 - lane;
+            unsigned w0[kTileWords], w1[kTileWords];
+            PtrCursor cur;
+            cur.seek(map, wq_hi);
 #pragma unroll
-            for (int w = 0; w < 8; ++w) words[w] = 0;
-            if (row >= 1) {
-                unsigned v[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int col = y - c;
-                    v[c] = (col >= 1) ? (unsigned)__ldcg(ptr + map.offset(row, col)) : 0u;
+            for (int q = kTileWords - 1; q >= 0; --q) {
+                const int wq = wq_hi - (kTileWords - 1 - q);
+                w0[q] = 0u; w1[q] = 0u;
+                if (wq >= 0) {
+                    if (row0 >= 1) w0[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row0)));
+                    if (row1 >= 1) w1[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row1)));
+                    if (wq > 0) cur.left(map);
                 }
-#pragma unroll
-                for (int c = 0; c < 32; ++c) words[c >> 2] |= v[c] << (8 * (c & 3));
             }
             __syncwarp();
 #pragma unroll
-            for (int w = 0; w < 8; ++w) tile[lane * kTileStride + w] = words[w];
+            for (int q = 0; q < kTileWords; ++q) {
+                tile[lane * kTileStride + q] = w0[q];
+                tile[(lane + 32) * kTileStride + q] = w1[q];
+            }
             __syncwarp();
             // ---- walk inside the tile -----------------------------------------------------
             if (lane == 0) {
-                int r = 0, c = 0;
-                while (r < 32 && c < 32 && x > 0 && y > 0) {
-                    const unsigned b = (tile[r * kTileStride + (c >> 2)] >> (8 * (c & 3))) & 0xFFu;
+                const int col_lo = (wq_hi - (kTileWords - 1)) * 4;      // 0-based column of tile word 0
+                int r = 0;
+                while (r < kTileRows && x > 0 && y > 0) {
+                    const int cw = (y - 1) - col_lo;
+                    if (cw < 0) break;
+                    const unsigned b = (tile[r * kTileStride + (cw >> 2)] >> (8 * (cw & 3))) & 0xFFu;
                     if (st < 0) st = 2 - (int)(b & 3u);                               // :102
-                    int op;
-                    if (st == 0)      { op = 0; st = 2 - (int)(b & 3u);        --x; --y; ++r; ++c; }  // :115-125
-                    else if (st == 1) { op = 1; st = 2 - (int)((b >> 2) & 3u); --x; ++r; }            // :128-135
-                    else              { op = 2; st = 2 - (int)((b >> 4) & 3u); --y; ++c; }            // :138-145
+                    // state 0: diagonal, next = mat_ptr; 1: x-gap, next = x_mat_ptr; 2: y-gap,
+                    // next = y_mat_ptr (:115-145) -- branch-free: the chain of dependent
+                    // instructions per path step is what bounds a whole-manuscript traceback
+                    const int dx = (st != 2), dy = (st != 1);
                     ++k;
-                    *(ops_end - k) = (uint8_t)op;
+                    *(ops_end - k) = (uint8_t)st;
+                    st = 2 - (int)((b >> (2 * st)) & 3u);
+                    x -= dx; r += dx; y -= dy;
                 }
             }
             x = __shfl_sync(kFull, x, 0);
@@ -424,7 +505,7 @@ template <bool SUBST, bool EYZ>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
 {
-    __shared__ unsigned tiles[kWarpsPerBlock][32 * kTileStride];
+    __shared__ unsigned tiles[kWarpsPerBlock][kTileRows * kTileStride];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * kWarpsPerBlock + warp;
@@ -465,7 +546,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
                 const int fin_k = last ? cc % C : -1;
                 dispatch_pass<SUBST, EYZ, false>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
                                                  ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap,
-                                                 nullptr, nullptr);
+                                                 Chain{nullptr, nullptr, 0, false});
                 __syncwarp();
             }
             // the lane that owns column m holds the corner scores
@@ -476,7 +557,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
         }
         __syncwarp();
         uint8_t *ops = a.ops + pd.ops_off;
-        const int L = traceback_warp(ptr, n, m, ops + (size_t)n + (size_t)m, tiles[warp], lane);
+        const int L = traceback_warp(ptr, n, m, kMaxC, ops + (size_t)n + (size_t)m, tiles[warp], lane);
         if (lane == 0) {
             a.ops_len[p] = L;
             if (a.scores) {
@@ -601,12 +682,11 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
                 if (cw < 0) break;
                 const unsigned b = (tile[r * kLineTile + (cw >> 2)] >> (8 * (cw & 3))) & 0xFFu;
                 if (st < 0) st = 2 - (int)(b & 3u);                                   // :102
-                int op;
-                if (st == 0)      { op = 0; st = 2 - (int)(b & 3u);        --x; --y; ++r; }   // :115-125
-                else if (st == 1) { op = 1; st = 2 - (int)((b >> 2) & 3u); --x; ++r; }        // :128-135
-                else              { op = 2; st = 2 - (int)((b >> 4) & 3u); --y; }             // :138-145
+                const int dx = (st != 2), dy = (st != 1);                             // :115-145
                 ++k;
-                *(ops_end - k) = (uint8_t)op;
+                *(ops_end - k) = (uint8_t)st;
+                st = 2 - (int)((b >> (2 * st)) & 3u);
+                x -= dx; r += dx; y -= dy;
             }
         }
         x = __shfl_sync(kFull, x, 0, kLineG);
@@ -747,30 +827,20 @@ align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
 // ---- one huge pair: chained passes ---------------------------------------------------------------
 // BASELINE config 5 (100k x 80k): a single pair must use the whole GPU.  Every pass (a stripe
 // of 32*C columns) gets its own warp, all passes are resident at once (cooperative launch), and
-// pass w consumes the right edge of pass w-1 through global memory about kPublishEvery rows
+// pass w consumes the right edge of pass w-1 through global memory a few rows
 // behind it -- a wavefront over stripes.  Pointers for the whole matrix stay in HBM
 // (1 byte/cell; 8 GB for config 5), and the ordinary tile-prefetch traceback runs afterwards.
 struct LongArgs {
     const uint8_t *T, *O;
     int n, m;
-    uint8_t *ptr;          // ptr_bytes(n, m)
-    int2 *bnd;             // (npass + 1) arrays of bnd_stride entries; array w = left edge of pass w
-    long long bnd_stride;
-    int *prog;             // npass + 1 progress counters; prog[0] = n once column 0 is written
-    int pass0;             // first pass handled by this launch (waves when passes > resident warps)
+    uint8_t *ptr;          // ptr_bytes(n, m, cfull)
+    int4 *chain;           // npass arrays of chain_stride records; array w = right edge of stripe w
+    long long chain_stride;
+    int epoch;             // nonzero, unique per launch within the context
+    int pass0;             // first stripe handled by this launch (waves when stripes > resident warps)
+    int cfull;             // stripe strip width: a full stripe has 32*cfull columns
     int *scores;           // 3 ints
 };
-
-__global__ void __launch_bounds__(256) long_init_kernel(const LongArgs a, const __grid_constant__ KParams kp)
-{
-    // left boundary of pass 0 = column 0: M = Y = bg*i, X = -inf (textSeqCompare.py:54-56)
-    const int stride = gridDim.x * blockDim.x;
-    for (int i = 1 + blockIdx.x * blockDim.x + threadIdx.x; i <= a.n + 1; i += stride)
-        a.bnd[i] = make_int2((kp.bg * i) | kTagM, kp.bg * i);
-    const int npass = (a.m + kPassW - 1) / kPassW;
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w <= npass; w += stride)
-        a.prog[w] = (w == 0) ? a.n : 0;       // column 0 is complete when this kernel ends
-}
 
 template <bool SUBST, bool EYZ>
 __global__ void __launch_bounds__(32, 8)
@@ -778,22 +848,25 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
 {
     const int w = a.pass0 + blockIdx.x;
     const int n = a.n, m = a.m;
-    const int nfull = m / kPassW, r = m % kPassW;
+    const int passw = 32 * a.cfull;
+    const int nfull = m / passw, r = m % passw;
     const int npass = nfull + (r ? 1 : 0);
     if (w >= npass) return;
-    const int C = (w < nfull) ? kMaxC : remainder_c(r);
-    const int j0 = w * kPassW;
+    const int C = (w < nfull) ? a.cfull : remainder_c(r);
+    const int j0 = w * passw;
     const bool last = (w == npass - 1);
     const int cc = m - 1 - j0;
     const int fin_lane = last ? cc / C : -1;
     const int fin_k = last ? cc % C : -1;
     int cap[3] = {0, 0, 0};
-    const long long pass_bytes = ((long long)n + 32) * kPassW;
-    dispatch_pass<SUBST, EYZ, true>(C, kp, a.T, a.O, n, m, j0, !last,
-                                    a.bnd + (size_t)w * (size_t)a.bnd_stride,
-                                    a.bnd + (size_t)(w + 1) * (size_t)a.bnd_stride,
-                                    a.ptr + (size_t)w * (size_t)pass_bytes, fin_lane, fin_k, cap,
-                                    a.prog + w, a.prog + w + 1);
+    const long long pass_bytes = ((long long)n + 32) * passw;
+    Chain ch;
+    ch.in = (w > 0) ? a.chain + (size_t)(w - 1) * (size_t)a.chain_stride : nullptr;
+    ch.out = a.chain + (size_t)w * (size_t)a.chain_stride;
+    ch.epoch = a.epoch;
+    ch.first = (w == 0);
+    dispatch_pass<SUBST, EYZ, true>(C, kp, a.T, a.O, n, m, j0, !last, nullptr, nullptr,
+                                    a.ptr + (size_t)w * (size_t)pass_bytes, fin_lane, fin_k, cap, ch);
     if (last && (int)(threadIdx.x & 31) == fin_lane && a.scores) {
         a.scores[0] = score_out(cap[0]);
         a.scores[1] = score_out(cap[1]);
@@ -802,11 +875,11 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
 }
 
 __global__ void __launch_bounds__(32)
-trace_long_kernel(const uint8_t *ptr, int n, int m, uint8_t *ops, int *ops_len)
+trace_long_kernel(const uint8_t *ptr, int n, int m, int cfull, uint8_t *ops, int *ops_len)
 {
-    __shared__ unsigned tile[32 * kTileStride];
+    __shared__ unsigned tile[kTileRows * kTileStride];
     const int lane = threadIdx.x & 31;
-    const int L = traceback_warp(ptr, n, m, ops + (size_t)n + (size_t)m, tile, lane);
+    const int L = traceback_warp(ptr, n, m, cfull, ops + (size_t)n + (size_t)m, tile, lane);
     if (lane == 0) *ops_len = L;
     const int shift = n + m - L;
     if (shift > 0) {
