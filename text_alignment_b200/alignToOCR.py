@@ -21,27 +21,24 @@ from . import textSeqCompare as tsc
 
 
 class CharBox(object):
-    """A character (or syllable) with its bounding box; ``ul``/``lr`` None marks a gap
-    (alignToOCR.py:35-58)."""
+    """A character (or syllable) with its bounding box; same attributes as the reference's
+    record (alignToOCR.py:35-58): ``ul``/``lr`` corner tuples (None marks a gap, and then the
+    scalar fields are left unset exactly as in the reference), ``ulx, uly, lrx, lry, width,
+    height``."""
     __slots__ = ['char', 'ul', 'lr', 'ulx', 'lrx', 'uly', 'lry', 'width', 'height']
 
     def __init__(self, char, ul=None, lr=None):
         self.char = char
-        if (ul is None) or (lr is None):
-            self.ul = None
-            self.lr = None
-            return
-        self.ul = tuple(ul)
-        self.lr = tuple(lr)
-        self.ulx, self.uly = ul[0], ul[1]
-        self.lrx, self.lry = lr[0], lr[1]
-        self.width = lr[0] - ul[0]
-        self.height = lr[1] - ul[1]
+        has_box = ul is not None and lr is not None
+        self.ul = tuple(ul) if has_box else None
+        self.lr = tuple(lr) if has_box else None
+        if has_box:
+            (self.ulx, self.uly), (self.lrx, self.lry) = (ul[0], ul[1]), (lr[0], lr[1])
+            self.width, self.height = lr[0] - ul[0], lr[1] - ul[1]
 
     def __repr__(self):
-        if self.ul and self.lr:
-            return '{}: {}, {}'.format(self.char, self.ul, self.lr)
-        return '{}: empty'.format(self.char)
+        where = '{}, {}'.format(self.ul, self.lr) if (self.ul and self.lr) else 'empty'
+        return '{}: {}'.format(self.char, where)
 
     def __eq__(self, other):
         return (isinstance(other, CharBox) and self.char == other.char and
@@ -81,34 +78,38 @@ def insert_gaps(all_chars, ocr_align):
     return [CharBox('_') if c == '_' else next(it) for c in ocr_align]
 
 
+def _syllable_pattern(syl):
+    """A syllable's letters with any number of gap symbols between them, exactly the regular
+    expression the reference builds (unescaped; alignToOCR.py:301-304)."""
+    if len(syl) == 1:
+        return syl
+    return syl[0] + syl[1:-1].replace('', '_*') + syl[-1]
+
+
 def syllable_boxes(transcript, tra_align, aligned_chars):
     """alignToOCR.py:277, :297-324: for every syllable of the transcript find, from a moving
     offset, the stretch of ``tra_align`` that spells it with optional gaps in between, and
-    union the boxes of the OCR characters aligned to that stretch."""
-    syls = latsyl.syllabify_text(transcript)
-    current_offset = 0
-    syl_boxes = []
-    for syl in syls:
-        if len(syl) < 1:
+    union the boxes of the OCR characters aligned to that stretch.  A syllable aligned to no
+    OCR character yields no box (:313); a syllable spanning two text lines keeps only the
+    boxes of the lower line (:318-320)."""
+    out = []
+    cursor = 0
+    for syl in latsyl.syllabify_text(transcript):
+        if not syl:
             continue
-        elif len(syl) == 1:
-            syl_regex = syl
-        else:
-            syl_regex = syl[0] + syl[1:-1].replace('', '_*') + syl[-1]      # unescaped, as :304
-        syl_match = re.search(syl_regex, tra_align[current_offset:])
-        start = syl_match.start() + current_offset
-        end = syl_match.end() + current_offset
-        current_offset = end
-        align_boxes = [x for x in aligned_chars[start:end] if x.lr is not None]
-        if not align_boxes:                      # aligned to nothing in the OCR (:313)
+        hit = re.search(_syllable_pattern(syl), tra_align[cursor:])
+        lo, hi = cursor + hit.start(), cursor + hit.end()
+        cursor = hi
+        boxed = [c for c in aligned_chars[lo:hi] if c.lr is not None]
+        if not boxed:
             continue
-        if len(set([x.uly for x in align_boxes])) > 1:        # spans text lines: keep the lower (:318-320)
-            lower_level = max(x.uly for x in align_boxes)
-            align_boxes = [b for b in align_boxes if b.uly == lower_level]
-        new_ul = (min(x.ulx for x in align_boxes), min(x.uly for x in align_boxes))
-        new_lr = (max(x.lrx for x in align_boxes), max(x.lry for x in align_boxes))
-        syl_boxes.append(CharBox(syl, new_ul, new_lr))
-    return syl_boxes
+        tops = set(c.uly for c in boxed)
+        if len(tops) > 1:
+            boxed = [c for c in boxed if c.uly == max(tops)]
+        out.append(CharBox(syl,
+                           (min(c.ulx for c in boxed), min(c.uly for c in boxed)),
+                           (max(c.lrx for c in boxed), max(c.lry for c in boxed))))
+    return out
 
 
 def boxes_for_page(transcript, all_chars, seq_align_params=None, device=0):
