@@ -132,6 +132,11 @@ int  tanw_batch_prepare(tanw_ctx *ctx,
                         const int64_t *o_off, const int32_t *m,
                         int64_t n_pairs, const tanw_scoring *scoring);
 int  tanw_batch_run(tanw_ctx *ctx);                       /* asynchronous on the ctx stream     */
+/* Replace the scoring system of the prepared batch; the sequences stay resident in HBM.  This
+ * is the reference's parameter sweep (evaluate_text_alignment.py:134-198: 729 integer scoring
+ * vectors over the same pages): prepare once, then { rescore, run, fetch } per vector.  An
+ * equality scorer may be replaced by another equality scorer, a table by a table of the same K. */
+int  tanw_batch_rescore(tanw_ctx *ctx, const tanw_scoring *scoring);
 int  tanw_batch_fetch(tanw_ctx *ctx,
                       uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
                       int32_t *ops_len, int32_t *scores);

@@ -149,6 +149,7 @@ def run_reference_process(A, transcript, boxes, params=None):
     """Unmodified alignToOCR.process with preprocessing / OCR patched out; angle 0."""
     import tempfile
     chars = [A.CharBox(c, ul, lr) for c, ul, lr in boxes]
+    saved = (A.preproc.preprocess_images, A.preproc.identify_text_lines, A.perform_ocr_with_ocropus)
     A.preproc.preprocess_images = lambda raw: (_Img(), None, 0.0)
     A.preproc.identify_text_lines = lambda image, eroded: ([], [100, 240, 380], None)
     A.perform_ocr_with_ocropus = lambda *a, **k: chars
@@ -158,6 +159,7 @@ def run_reference_process(A, transcript, boxes, params=None):
         return A.process(_Img(), transcript, 'nomodel', seq_align_params=params, wkdir_name='wk')
     finally:
         os.chdir(cwd)
+        A.preproc.preprocess_images, A.preproc.identify_text_lines, A.perform_ocr_with_ocropus = saved
 
 
 def consumer_golden():

@@ -121,3 +121,44 @@ def test_pages_golden_on_gpu(golden):
     for page in golden['pages']:
         syl_boxes, _, _, _ = atocr.boxes_for_page(page['transcript'], _boxes(page), page['params'])
         assert _as_tuples(syl_boxes) == page['syl_boxes']
+
+
+# ---- wire format: OCRopus .llocs -> CharBox (alignToOCR.py:153-182) -------------------------------
+
+LLOCS = [u'g\t12.4\n', u'l\t20.0\n', u'~\t22.5\n', u'o\t31.6\n', u'\t33.0\n', u'r\t40.49\n', u'ū\t55.5\n', u'a\t70.51\n']
+
+
+def test_parse_llocs_right_edges_become_boxes():
+    chars, other = atocr.parse_llocs(LLOCS, 100, 50, 110)
+    assert ''.join(c.char for c in chars) == u'glorūa'
+    assert [(c.ul, c.lr) for c in chars][:3] == [((100, 50), (112, 110)), ((112, 50), (120, 110)), ((122, 50), (132, 110))]
+    assert [c.char for c in other] == ['~', ''] and other[0].ul == (120, 50)
+    assert chars[-1].lr == (171, 110)          # np.round(70.51 + 100)
+
+
+def test_parse_llocs_matches_reference_ocr_reader(tmp_path, monkeypatch):
+    """Drive the reference's perform_ocr_with_ocropus with the subprocess patched out and
+    .llocs files prepared on disk; our reader must produce the same boxes."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference checkout not present')
+    A = ref_loader.load_aligntoocr()
+
+    class Strip(object):
+        def __init__(self, ox, oy, h):
+            self.offset_x, self.offset_y, self.height = ox, oy, h
+
+        def save_image(self, path):
+            pass
+    strips = [Strip(100, 50, 60), Strip(90, 190, 58)]
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / 'wk').mkdir()
+    import io
+    for i, recs in enumerate([LLOCS, [u'd\t9.5\n', u'n\t19.5\n', u's\t30.2\n', u'~\t31.0\n']]):
+        with io.open(str(tmp_path / 'wk' / '_{}.llocs'.format(i)), 'w', encoding='utf-8') as f:
+            f.writelines(recs)
+    monkeypatch.setattr(A.subprocess, 'check_call', lambda *a, **k: 0)
+    ref = A.perform_ocr_with_ocropus(strips, 'nomodel', 'wk')
+    got = atocr.read_llocs_files([str(tmp_path / 'wk' / '_{}.llocs'.format(i)) for i in range(2)],
+                                 [(s.offset_x, s.offset_y, s.height) for s in strips])
+    assert [(c.char, tuple(c.ul), tuple(c.lr)) for c in ref] == [(c.char, c.ul, c.lr) for c in got]

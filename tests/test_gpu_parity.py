@@ -358,3 +358,21 @@ def test_line_kernel_general_gap_extend_and_callable(tsc, oracle):
     got = tsc.perform_alignment(list(t), list(o), scoring_system=system, return_scores=True)
     want = oracle.perform_alignment(list(t), list(o), system, full=True)
     assert (got[0], got[1]) == (want[0], want[1]) and tuple(got[2]) == _end(want[2]['end'])
+
+
+def test_parameter_sweep_resident_sequences(tsc, oracle):
+    """evaluate_text_alignment.py:181-188: the same pages under many scoring vectors; the
+    sequences are uploaded once and every vector is one rescore + launch."""
+    from itertools import product
+    grid = list(product([5, 8, 11], [-4, -7, -10], [-2, -5, -7], [-2, -5, -7], [0, -3, -5], [0, -3, -5]))
+    rng = random.Random(3)
+    systems = [list(p) for p in rng.sample(grid, 20)] + [[10, -5, -7, -7]]
+    pairs = [(list(t), list(o)) for t, o in (synth.make_pair(900 + k, 150 + 30 * k, 200 + 25 * k, 2, 20) for k in range(3))]
+    pairs.append((list('dominus'), list('dns')))
+    got = tsc.perform_alignment_sweep(pairs, systems, return_scores=True)
+    assert len(got) == len(systems)
+    for system, res in zip(systems, got):
+        for (T, O), (tra, ocr, score) in zip(pairs, res):
+            want = oracle.perform_alignment(T, O, system, full=True)
+            assert (tra, ocr) == (want[0], want[1]), system
+            assert tuple(score) == _end(want[2]['end'])

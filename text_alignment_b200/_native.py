@@ -55,6 +55,7 @@ SIGNATURES = {
     'tanw_batch_prepare': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                           ctypes.POINTER(Scoring)]),
     'tanw_batch_run': (ctypes.c_int, [_VOIDP]),
+    'tanw_batch_rescore': (ctypes.c_int, [_VOIDP, ctypes.POINTER(Scoring)]),
     'tanw_batch_fetch': (ctypes.c_int, [_VOIDP, _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
     'tanw_sync': (ctypes.c_int, [_VOIDP]),
     'tanw_last_timing': (ctypes.c_int, [_VOIDP, ctypes.POINTER(Timing)]),
@@ -221,6 +222,12 @@ class Context(object):
         self._check(self._lib.tanw_batch_prepare(self._h, _ptr(symbols, _u8p), symbols.size, _ptr(t_off, _i64p),
                                                  _ptr(n, _i32p), _ptr(o_off, _i64p), _ptr(m, _i32p), int(n.size),
                                                  ctypes.byref(sc)))
+
+    def rescore(self, scoring):
+        """New scoring system for the prepared batch (sequences stay resident in HBM)."""
+        sc, keep = scoring
+        self._keep = self._keep[:5] + (sc, keep)
+        self._check(self._lib.tanw_batch_rescore(self._h, ctypes.byref(sc)))
 
     def run(self):
         self._check(self._lib.tanw_batch_run(self._h))

@@ -142,3 +142,40 @@ def to_JSON_dict(syl_boxes, lines_peak_locs):
                                   'ul': [int(s.ul[0]), int(s.ul[1])],
                                   'lr': [int(s.lr[0]), int(s.lr[1])]})
     return data
+
+
+# ---- wire formats either side of the path --------------------------------
+
+def clean_special_chars(inp):
+    """alignToOCR.py:61-72: OCRopus' '~' never reaches the aligner."""
+    return inp.replace('~', '')
+
+
+def parse_llocs(lines, x_min, y_min, y_max):
+    """One text line of OCRopus ``--llocs`` output -> CharBoxes (alignToOCR.py:153-182).
+
+    Each TSV record is (character, x position of its RIGHT edge inside the strip); a
+    character's box therefore runs from the previous record's x to its own x, over the
+    strip's full height.  Records whose character is '~' or empty advance the x position but
+    are set aside (returned second)."""
+    chars, other = [], []
+    prev_x = x_min
+    for rec in lines:
+        fields = rec.rstrip('\n').split('\t')
+        cur_x = int(np.round(float(fields[1]) + x_min))
+        box = CharBox(fields[0] if fields[0] in ('~', '') else clean_special_chars(fields[0]),
+                      (prev_x, y_min), (cur_x, y_max))
+        (other if fields[0] in ('~', '') else chars).append(box)
+        prev_x = cur_x
+    return chars, other
+
+
+def read_llocs_files(paths, strips):
+    """All text lines of a page: ``strips[i]`` gives (offset_x, offset_y, height) of line i."""
+    import io
+    all_chars = []
+    for path, (off_x, off_y, height) in zip(paths, strips):
+        with io.open(path, encoding='utf-8') as f:
+            chars, _ = parse_llocs(list(f), off_x, off_y, off_y + height)
+        all_chars += chars
+    return all_chars

@@ -57,6 +57,7 @@ struct tanw_ctx {
                 ev_d2h0 = nullptr, ev_d2h1 = nullptr;
     std::string err;
     int64_t arena_limit = 0;
+    int64_t max_nm = 0;                   // largest n+m of the prepared batch (range check on rescore)
     int64_t total_mem = 0;
 
     DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_prog, d_quads;
@@ -128,6 +129,37 @@ bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
     if (s->subst)
         for (int64_t i = 0; i < (int64_t)s->subst_k * s->subst_k; ++i) upd(s->subst[i]);
     return (max_n_plus_m + 2) * pmax < (int64_t(1) << 25);
+}
+
+void fill_kparams(KParams &kp, const tanw_scoring *sc)
+{
+    const int *keep_tab = kp.subst;
+    const int keep_k = kp.subst_k;
+    memset(&kp, 0, sizeof kp);
+    kp.maT = (sc->match << kShift) | kTagM;
+    kp.miT = (sc->mismatch << kShift) | kTagM;
+    kp.ox = (sc->gap_open_x + sc->gap_extend_x) * (1 << kShift);
+    kp.ex = sc->gap_extend_x * (1 << kShift);
+    kp.oy = (sc->gap_open_y + sc->gap_extend_y) * (1 << kShift);
+    kp.ey = sc->gap_extend_y * (1 << kShift);
+    kp.bg = sc->boundary_gap * (1 << kShift);
+    kp.subst = keep_tab;
+    kp.subst_k = keep_k;
+}
+
+int upload_subst(tanw_ctx *ctx, const tanw_scoring *sc, int64_t *h2d)
+{
+    const size_t kk = (size_t)sc->subst_k * (size_t)sc->subst_k;
+    std::vector<int> tab(kk);
+    for (size_t i = 0; i < kk; ++i) tab[i] = (sc->subst[i] * (1 << kShift)) | kTagM;
+    if (ctx->d_subst.reserve(sizeof(int) * kk) != cudaSuccess)
+        return fail(ctx, TANW_E_NOMEM, "device allocation failed (substitution table)");
+    TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_subst.p, tab.data(), sizeof(int) * kk, cudaMemcpyHostToDevice, ctx->stream));
+    TANW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // tab is a local
+    ctx->kp.subst = (const int *)ctx->d_subst.p;
+    ctx->kp.subst_k = sc->subst_k;
+    if (h2d) *h2d += (int64_t)(sizeof(int) * kk);
+    return TANW_OK;
 }
 
 // The chain records carry an epoch stamp; fresh memory must not contain a live one.
@@ -476,16 +508,9 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     }
 
     // ---- kernel parameters ------------------------------------------------------------------
-    KParams &kp = ctx->kp;
-    memset(&kp, 0, sizeof kp);
-    kp.maT = (sc->match << kShift) | kTagM;
-    kp.miT = (sc->mismatch << kShift) | kTagM;
-    kp.ox = (sc->gap_open_x + sc->gap_extend_x) * (1 << kShift);
-    kp.ex = sc->gap_extend_x * (1 << kShift);
-    kp.oy = (sc->gap_open_y + sc->gap_extend_y) * (1 << kShift);
-    kp.ey = sc->gap_extend_y * (1 << kShift);
-    kp.bg = sc->boundary_gap * (1 << kShift);
+    fill_kparams(ctx->kp, sc);
     ctx->use_subst = sc->subst != nullptr;
+    ctx->max_nm = max_nm;
 
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
 
@@ -551,16 +576,8 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         h2d += (int64_t)sizeof(PairDesc) * n_pairs + (int64_t)sizeof(int) * n_batch + (int64_t)sizeof(int4) * n_quads;
     }
     if (ctx->use_subst) {
-        const size_t kk = (size_t)sc->subst_k * (size_t)sc->subst_k;
-        std::vector<int> tab(kk);
-        for (size_t i = 0; i < kk; ++i) tab[i] = (sc->subst[i] * (1 << kShift)) | kTagM;
-        if (ctx->d_subst.reserve(sizeof(int) * kk) != cudaSuccess)
-            return fail(ctx, TANW_E_NOMEM, "device allocation failed (substitution table)");
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_subst.p, tab.data(), sizeof(int) * kk, cudaMemcpyHostToDevice, ctx->stream));
-        TANW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // tab is a local
-        kp.subst = (const int *)ctx->d_subst.p;
-        kp.subst_k = sc->subst_k;
-        h2d += (int64_t)(sizeof(int) * kk);
+        int rc = upload_subst(ctx, sc, &h2d);
+        if (rc) return rc;
     }
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d1, ctx->stream));
 
@@ -598,6 +615,28 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     ctx->timing.h2d_bytes = h2d;
     ctx->timing.host_prepare_ms = host_timer.ms();
     ctx->prepared = true;
+    return TANW_OK;
+}
+
+int tanw_batch_rescore(tanw_ctx *ctx, const tanw_scoring *sc)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    if (!ctx->prepared) return fail(ctx, TANW_E_STATE, "tanw_batch_rescore before tanw_batch_prepare");
+    if (!sc) return fail(ctx, TANW_E_INVALID, "scoring is NULL");
+    if ((sc->subst != nullptr) != ctx->use_subst)
+        return fail(ctx, TANW_E_INVALID, "rescore cannot switch between an equality scorer and a table");
+    if (sc->subst && sc->subst_k != ctx->kp.subst_k)
+        return fail(ctx, TANW_E_INVALID, "rescore needs a table of the same size (K = %d)", ctx->kp.subst_k);
+    if (!scoring_in_range(sc, ctx->max_nm))
+        return fail(ctx, TANW_E_RANGE,
+                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^25");
+    TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+    fill_kparams(ctx->kp, sc);
+    if (sc->subst) {
+        int rc = upload_subst(ctx, sc, nullptr);
+        if (rc) return rc;
+    }
+    ctx->ran = false;
     return TANW_OK;
 }
 

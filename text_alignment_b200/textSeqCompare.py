@@ -302,6 +302,61 @@ def perform_alignment_batch(pairs, scoring_system=None, devices=None, return_sco
     return final
 
 
+def perform_alignment_sweep(pairs, scoring_systems, device=0, return_scores=False):
+    """The reference's parameter sweep (evaluate_text_alignment.py:134-198 re-aligns the same
+    pages under 729 scoring vectors): the pairs are encoded and uploaded once, then every
+    numeric scoring system costs one launch.  Returns one result list (as
+    ``perform_alignment_batch``) per scoring system."""
+    pairs = list(pairs)
+    for t, o in pairs:
+        _check_list(t, 'transcript')
+        _check_list(o, 'ocr')
+    parsed = [parse_scoring_system(s) for s in scoring_systems]
+    if any(p[0] is not None for p in parsed):
+        return [perform_alignment_batch(pairs, s, devices=[device], return_scores=return_scores)
+                for s in scoring_systems]
+    boundary = _as_int(gap_extend, 'gap_extend')
+    encs = [_encode_pair(t, o, need_dense=False) for t, o in pairs]
+    if not all(e.reflexive for e in encs):
+        return [perform_alignment_batch(pairs, s, devices=[device], return_scores=return_scores)
+                for s in scoring_systems]
+    symbols, t_off, n, o_off, m = _pack_encoded(encs)
+    ctx = get_context(device)
+    out = []
+    for k, (_, match, mismatch, gox, goy, gex, gey) in enumerate(parsed):
+        scoring = ctx.make_scoring(match, mismatch, gox, goy, gex, gey, boundary)
+        if k == 0:
+            ctx.prepare(symbols, t_off, n, o_off, m, scoring)
+        else:
+            ctx.rescore(scoring)
+        ctx.run()
+        ops, ops_off, ops_len, scores = ctx.fetch()
+        res = []
+        for i in range(len(pairs)):
+            tra, oc = _decode(pairs[i][0], pairs[i][1], ops[ops_off[i]:ops_off[i] + ops_len[i]], encs[i])
+            item = (tra, oc)
+            if return_scores:
+                item += (tuple(None if v == _native.NEG_INF else int(v) for v in scores[i].tolist()),)
+            res.append(item)
+        out.append(res)
+    return out
+
+
+def _pack_encoded(encs):
+    n = np.asarray([e.t_codes.size for e in encs], dtype=np.int32)
+    m = np.asarray([e.o_codes.size for e in encs], dtype=np.int32)
+    parts = []
+    for e in encs:
+        parts.append(e.t_codes)
+        parts.append(e.o_codes)
+    symbols = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+    lens = n.astype(np.int64) + m.astype(np.int64)
+    t_off = np.zeros(len(encs), dtype=np.int64)
+    if len(encs):
+        np.cumsum(lens[:-1], out=t_off[1:])
+    return symbols, t_off, n, t_off + n, m
+
+
 def _run_group(encs, params, subst, devices):
     n = np.asarray([e.t_codes.size for e in encs], dtype=np.int32)
     m = np.asarray([e.o_codes.size for e in encs], dtype=np.int32)
