@@ -132,10 +132,23 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
     for (int k = 0; k < C; ++k) {
         int sc;
         if (SUBST) sc = __ldg(srow + s.oc[k]);
-        else       sc = (s.oc[k] == tch) ? kp.maT : kp.miT;                      // :31-32
+        else       sc = 0;                                                        // :31-32 below
         // M[i][j] = max(M,X,Y)[i-1][j-1] + score, tagged as an M value         (:70-72)
         const int dc = clean_tag(dul);
-        const int m2 = dc + sc;
+        int m2;
+        if (SUBST) {
+            m2 = dc + sc;
+        } else {
+            // compare + add + predicated add instead of compare + select + add: ptxas turns the
+            // two adds into VIADD, which B200 issues on whichever of the alu / fma pipes is free
+            // (profiles/r1_int32_pipes.txt), so the saturated alu pipe loses one op per cell
+            // (measured +10 % on config 2)
+            asm("{ .reg .pred p;\n\t"
+                "setp.eq.s32 p, %1, %2;\n\t"
+                "add.s32 %0, %3, %4;\n\t"
+                "@p add.s32 %0, %3, %5; }"
+                : "=r"(m2) : "r"(s.oc[k]), "r"(tch), "r"(dc), "r"(kp.miT), "r"(kp.maT));
+        }
         // X[i][j] = max(M[i-1][j]+ox, X[i-1][j]+ex, Y[i-1][j]+ox)               (:83-88)
         const int xraw = __viaddmax_s32(s.W[k], cx, s.Xh[k]);
         const int xh = clean_tag_or(xraw, kTagX);
