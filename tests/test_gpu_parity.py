@@ -225,7 +225,7 @@ def test_c2_sample_pages_bit_exact(tsc, oracle):
 
 
 def test_c3_lines_bit_exact(tsc, oracle):
-    pairs = [synth.c3_pair(k) for k in range(3000)]
+    pairs = [synth.c3_pair(k) for k in range(10000)]
     _check_packed_vs_oracle(tsc, oracle, pairs)
 
 
@@ -376,3 +376,27 @@ def test_parameter_sweep_resident_sequences(tsc, oracle):
             want = oracle.perform_alignment(T, O, system, full=True)
             assert (tra, ocr) == (want[0], want[1]), system
             assert tuple(score) == _end(want[2]['end'])
+
+
+def test_c2_all_10k_pages_bit_exact(tsc, oracle):
+    """The north-star gate: all 10 000 seeded page pairs of BASELINE config 2, op strings and
+    corner scores bit-exact against the C oracle (which is itself pinned to the reference)."""
+    import os
+    import bench
+    cores = len(os.sched_getaffinity(0))
+    packed, _ = bench.make_workload('c2', 0, 10000, max(1, min(cores, 32)))
+    buf, t_off, n, o_off, m = packed
+    ops, ops_off, ops_len, scores = tsc.align_packed(buf, t_off, n, o_off, m, DEFAULT)
+    sc, _ = oracle.make_scoring(list(DEFAULT[:6]), boundary_gap=DEFAULT[6])
+    r_ops, r_off, r_len, r_end = oracle.align_batch_codes(buf, t_off, n, o_off, m, sc, threads=cores)
+    assert np.array_equal(ops_len, r_len) and np.array_equal(ops_off, r_off)
+    assert np.array_equal(scores.astype(np.float64), np.where(r_end <= -1e99, -1073741824, r_end))
+    used = np.zeros(ops.size, dtype=bool)
+    idx = np.concatenate([np.arange(o, o + l) for o, l in zip(ops_off.tolist(), ops_len.tolist())])
+    used[idx] = True
+    assert np.array_equal(ops[used], r_ops[used])
+
+
+def test_c4_256_pages_bit_exact(tsc, oracle):
+    pairs = [synth.c4_pair(100 + k) for k in range(256)]
+    _check_packed_vs_oracle(tsc, oracle, pairs, threads=16)

@@ -95,41 +95,51 @@ class _Encoded(object):
     __slots__ = ('t_codes', 'o_codes', 'symbols', 't_cp', 'o_cp', 'reflexive')
 
 
-def _all_single_chars(seq):
+def _code_points(seq):
+    """uint32 code points of a list of 1-character strings, or None if the list holds anything
+    else (other types, longer or empty strings).  Everything runs at C speed: joining with a
+    NUL separator fails for non-strings, and the result has the separators at exactly the odd
+    positions iff every element is one character long."""
+    k = len(seq)
+    if k == 0:
+        return np.zeros(0, dtype=np.uint32)
     try:
-        return all(type(e) is str for e in seq) and set(map(len, seq)) <= {1}
+        joined = '\x00'.join(seq)
     except TypeError:
-        return False
+        return None
+    chars = joined[0::2]
+    if len(joined) != 2 * k - 1 or joined[1::2] != '\x00' * (k - 1) or '\x00' in chars:
+        return None
+    try:
+        return np.frombuffer(chars.encode('utf-32-le', 'surrogatepass'), dtype=np.uint32)
+    except UnicodeError:
+        return None
 
 
 def _encode_pair(transcript, ocr, need_dense):
     enc = _Encoded()
     enc.reflexive = True
     enc.t_cp = enc.o_cp = None
-    if _all_single_chars(transcript) and _all_single_chars(ocr):
-        # production case (alignToOCR.py:273: list(transcript), list(ocr)): go through UTF-32
-        try:
-            t_cp = np.frombuffer(''.join(transcript).encode('utf-32-le', 'surrogatepass'), dtype=np.uint32)
-            o_cp = np.frombuffer(''.join(ocr).encode('utf-32-le', 'surrogatepass'), dtype=np.uint32)
-        except UnicodeError:
-            t_cp = None
-        if t_cp is not None:
-            enc.t_cp, enc.o_cp = t_cp, o_cp
-            top = int(max(t_cp.max() if t_cp.size else 0, o_cp.max() if o_cp.size else 0))
-            if top < 256 and not need_dense:
-                enc.t_codes = t_cp.astype(np.uint8)
-                enc.o_codes = o_cp.astype(np.uint8)
-                enc.symbols = None
-                return enc
-            both = np.concatenate([t_cp, o_cp])
-            uniq, inv = np.unique(both, return_inverse=True)
-            if uniq.size > 256:
-                raise ValueError('more than 256 distinct symbols in one pair ({}); the uint8 device path '
-                                 'cannot represent them'.format(uniq.size))
-            enc.t_codes = inv[:t_cp.size].astype(np.uint8)
-            enc.o_codes = inv[t_cp.size:].astype(np.uint8)
-            enc.symbols = [chr(c) for c in uniq.tolist()]
+    # production case (alignToOCR.py:273: list(transcript), list(ocr)): single characters
+    t_cp = _code_points(transcript)
+    o_cp = _code_points(ocr) if t_cp is not None else None
+    if o_cp is not None:
+        enc.t_cp, enc.o_cp = t_cp, o_cp
+        top = int(max(t_cp.max() if t_cp.size else 0, o_cp.max() if o_cp.size else 0))
+        if top < 256 and not need_dense:
+            enc.t_codes = t_cp.astype(np.uint8)
+            enc.o_codes = o_cp.astype(np.uint8)
+            enc.symbols = None
             return enc
+        both = np.concatenate([t_cp, o_cp])
+        uniq, inv = np.unique(both, return_inverse=True)
+        if uniq.size > 256:
+            raise ValueError('more than 256 distinct symbols in one pair ({}); the uint8 device path '
+                             'cannot represent them'.format(uniq.size))
+        enc.t_codes = inv[:t_cp.size].astype(np.uint8)
+        enc.o_codes = inv[t_cp.size:].astype(np.uint8)
+        enc.symbols = [chr(c) for c in uniq.tolist()]
+        return enc
     # general elements (e.g. the 2-character strings of the reference's demo, :185-186)
     table = {}
     symbols = []
