@@ -396,6 +396,17 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     if (sc->subst && (sc->subst_k < 1 || sc->subst_k > 256))
         return fail(ctx, TANW_E_INVALID, "subst_k must be in 1..256");
 
+    // ---- start the symbol upload first: it overlaps the host-side table building below (the
+    // copy is asynchronous when the caller's buffer is pinned) -------------------------------
+    TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->d_sym.reserve((size_t)symbols_len + 16) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, TANW_E_NOMEM, "device allocation failed (symbols, %lld bytes)", (long long)symbols_len);
+    }
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d0, ctx->stream));
+    if (symbols_len > 0)
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sym.p, symbols, (size_t)symbols_len, cudaMemcpyHostToDevice, ctx->stream));
+
     // ---- pair table, canonical op layout, size statistics --------------------------------
     ctx->h_pairs.resize((size_t)n_pairs);
     ctx->h_ops_off.resize((size_t)n_pairs);
@@ -544,8 +555,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     const int bnd_rows = max_n + 4;      // bnd[1..n] plus the prefetch overrun
 
     // ---- device buffers and uploads -------------------------------------------------------
-    if (ctx->d_sym.reserve((size_t)symbols_len + 16) != cudaSuccess ||
-        ctx->d_pairs.reserve(sizeof(PairDesc) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
+    if (ctx->d_pairs.reserve(sizeof(PairDesc) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_order.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_counter.reserve(256) != cudaSuccess ||
         ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(std::max(slots * slot_bytes, max_long), line_arena), 256)) != cudaSuccess ||
@@ -558,12 +568,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         cudaGetLastError();
         return fail(ctx, TANW_E_NOMEM, "device allocation failed (arena %lld bytes)", (long long)(slots * slot_bytes));
     }
-    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d0, ctx->stream));
-    int64_t h2d = 0;
-    if (symbols_len > 0) {
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sym.p, symbols, (size_t)symbols_len, cudaMemcpyHostToDevice, ctx->stream));
-        h2d += symbols_len;
-    }
+    int64_t h2d = symbols_len;
     if (n_pairs > 0) {
         TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairDesc) * (size_t)n_pairs,
                                        cudaMemcpyHostToDevice, ctx->stream));
