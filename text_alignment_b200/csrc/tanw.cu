@@ -81,6 +81,7 @@ struct tanw_ctx {
     int64_t n_pairs = 0, ops_total = 0;
     KParams kp;
     bool use_subst = false;
+    bool opens_nonpositive = false;       // gap_open_x <= 0 and gap_open_y <= 0
     BatchArgs args;
     int grid = 0;
     int occ_plain = 0, occ_subst = 0;
@@ -162,6 +163,15 @@ int upload_subst(tanw_ctx *ctx, const tanw_scoring *sc, int64_t *h2d)
     return TANW_OK;
 }
 
+// Which instantiation serves the prepared scoring system: -1 substitution table, 0 general,
+// 1 gap opens <= 0, 2 gap opens <= 0 and gap_extend_y == 0.
+int kernel_variant(const tanw_ctx *ctx)
+{
+    if (ctx->use_subst) return -1;
+    if (!ctx->opens_nonpositive) return 0;
+    return ctx->kp.ey == 0 ? 2 : 1;
+}
+
 // The chain records carry an epoch stamp; fresh memory must not contain a live one.
 cudaError_t reserve_zeroed(tanw_ctx *ctx, DevBuf &buf, size_t bytes)
 {
@@ -213,9 +223,11 @@ int run_long_pair(tanw_ctx *ctx, int p, int *launches)
         la.pass0 = w0;
         const int grid = std::min(ctx->long_capacity, npass - w0);
         void *args[] = { (void *)&la, (void *)&ctx->kp };
-        const void *fn = ctx->use_subst ? (const void *)align_long_kernel<true, false>
-                       : (ctx->kp.ey == 0 ? (const void *)align_long_kernel<false, true>
-                                          : (const void *)align_long_kernel<false, false>);
+        const int var = kernel_variant(ctx);
+        const void *fn = var < 0 ? (const void *)align_long_kernel<true, 0>
+                       : var == 2 ? (const void *)align_long_kernel<false, 2>
+                       : var == 1 ? (const void *)align_long_kernel<false, 1>
+                                  : (const void *)align_long_kernel<false, 0>;
         TANW_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(32), args, 0, ctx->stream));
         ++*launches;
     }
@@ -301,10 +313,10 @@ int tanw_create(int device, tanw_ctx **out)
     for (auto ev : evs)
         if (e == cudaSuccess) e = cudaEventCreate(ev);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_plain, align_pairs_kernel<false, false>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_plain, align_pairs_kernel<false, 2>,
                                                           kWarpsPerBlock * 32, 0);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_subst, align_pairs_kernel<true, false>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_subst, align_pairs_kernel<true, 0>,
                                                           kWarpsPerBlock * 32, 0);
     if (e != cudaSuccess) {
         int rc = fail(nullptr, TANW_E_CUDA, "context setup on device %d: %s", device, cudaGetErrorString(e));
@@ -313,11 +325,11 @@ int tanw_create(int device, tanw_ctx **out)
     }
     if (ctx->occ_plain < 1) ctx->occ_plain = 1;
     if (ctx->occ_subst < 1) ctx->occ_subst = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_line, align_lines_kernel<true, false>, kWarpsPerBlock * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_line, align_lines_kernel<true, 0>, kWarpsPerBlock * 32, 0);
     if (ctx->occ_line < 1) ctx->occ_line = 1;
     {
         int occ_long = 0, coop = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, align_long_kernel<true, false>, 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, align_long_kernel<true, 0>, 32, 0);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         ctx->long_capacity = coop ? std::max(1, occ_long) * ctx->sm_count : 0;
         cudaGetLastError();
@@ -521,6 +533,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     // ---- kernel parameters ------------------------------------------------------------------
     fill_kparams(ctx->kp, sc);
     ctx->use_subst = sc->subst != nullptr;
+    ctx->opens_nonpositive = sc->gap_open_x <= 0 && sc->gap_open_y <= 0;
     ctx->max_nm = max_nm;
 
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -637,6 +650,7 @@ int tanw_batch_rescore(tanw_ctx *ctx, const tanw_scoring *sc)
                     "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^25");
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
     fill_kparams(ctx->kp, sc);
+    ctx->opens_nonpositive = sc->gap_open_x <= 0 && sc->gap_open_y <= 0;
     if (sc->subst) {
         int rc = upload_subst(ctx, sc, nullptr);
         if (rc) return rc;
@@ -657,24 +671,25 @@ int tanw_batch_run(tanw_ctx *ctx)
         TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 2 * sizeof(unsigned), ctx->stream));
     if (ctx->largs.n_quads > 0) {
         const int threads = kWarpsPerBlock * 32;
-        if (ctx->use_subst)
-            align_lines_kernel<true, false><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp);
-        else if (ctx->kp.ey == 0)
-            align_lines_kernel<false, true><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp);
-        else
-            align_lines_kernel<false, false><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp);
+        switch (kernel_variant(ctx)) {
+        case -1: align_lines_kernel<true, 0><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp); break;
+        case 2:  align_lines_kernel<false, 2><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp); break;
+        case 1:  align_lines_kernel<false, 1><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp); break;
+        default: align_lines_kernel<false, 0><<<ctx->line_grid, threads, 0, ctx->stream>>>(ctx->largs, ctx->kp); break;
+        }
         TANW_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
     if (ctx->args.n_pairs > 0) {
-        // three instantiations: tabulated scorer; equality scorer; equality scorer with
-        // gap_extend_y == 0 (the reference's default_sys), which drops one add per cell
-        if (ctx->use_subst)
-            align_pairs_kernel<true, false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
-        else if (ctx->kp.ey == 0)
-            align_pairs_kernel<false, true><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
-        else
-            align_pairs_kernel<false, false><<<ctx->grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->args, ctx->kp);
+        // tabulated scorer; general equality scorer; gap opens <= 0; gap opens <= 0 and
+        // gap_extend_y == 0 (the reference's default_sys) -- see Strip in tanw_kernels.cuh
+        const int threads = kWarpsPerBlock * 32;
+        switch (kernel_variant(ctx)) {
+        case -1: align_pairs_kernel<true, 0><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+        case 2:  align_pairs_kernel<false, 2><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+        case 1:  align_pairs_kernel<false, 1><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+        default: align_pairs_kernel<false, 0><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+        }
         TANW_CUDA(ctx, cudaGetLastError());
         ++launches;
     }

@@ -103,9 +103,17 @@ __device__ __forceinline__ int clean_tag_or(int v, int tag)
     return r;
 }
 
+// Kernel variants (template parameter VAR):
+//   0  general: any gap parameters.  Keeps W = max(M,Y), Q = max(M,X) and D = max(M,X,Y).
+//   1  gap_open_x <= 0 and gap_open_y <= 0 (every scoring system the reference ships or sweeps):
+//      then max(M,Y)+ox vs X+ex and max(M,X)+oy vs Y+ey can both be taken from D = max(M,X,Y):
+//      the extra candidate (X+ox resp. Y+oy) never beats X+ex resp. Y+ey and never changes the
+//      first-index argmax (case analysis in DESIGN.md 4.1).  W and Q disappear: two maxes and
+//      one register per column less, D is one VIMNMX3.
+//   2  variant 1 with gap_extend_y == 0 (the reference's default_sys): no Y + ey add.
 template <int C>
 struct Strip {
-    int W[C];         // max(M|tagM, Y) of the row above, real value
+    int W[C];         // general variant only: max(M|tagM, Y) of the row above
     int Xh[C];        // X^ = (X|tagX) - ex*i of the row above
     int D[C];         // max(M, X, Y) tagged, of the row above
     int oc[C];        // the strip's OCR symbols
@@ -117,32 +125,31 @@ struct Strip {
 //   xe, cx     : ex*i and ox - ex*i for this lane's row i
 // Returns the strip's right edge in q_out / y_out and the C pointer bytes in pw[C/4].
 // EYZ: gap_extend_y == 0 (the reference's default_sys), which saves the Y + ey add.
-template <int C, bool FINAL, bool SUBST, bool EYZ>
+template <int C, bool FINAL, bool SUBST, int VAR>
 __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tch, int xe, int cx,
                                           int q_in, int y_in, int dul_in,
                                           int &q_out, int &y_out, unsigned (&pw)[C / 4],
                                           int kfin, int (&cap)[3])
 {
+    constexpr bool FAST = (VAR >= 1);
+    constexpr bool EYZ = (VAR == 2);
     const int *srow = SUBST ? kp.subst + tch * kp.subst_k : nullptr;
-    int q = q_in;
+    int q = q_in;                             // general: Q of the cell to the left; FAST: its D
     int ypl = EYZ ? y_in : y_in + kp.ey;      // Y of the column to the left, + ey
     int dul = dul_in;
     int acc = 0;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        int sc;
-        if (SUBST) sc = __ldg(srow + s.oc[k]);
-        else       sc = 0;                                                        // :31-32 below
         // M[i][j] = max(M,X,Y)[i-1][j-1] + score, tagged as an M value         (:70-72)
         const int dc = clean_tag(dul);
         int m2;
         if (SUBST) {
-            m2 = dc + sc;
+            m2 = dc + __ldg(srow + s.oc[k]);
         } else {
             // compare + add + predicated add instead of compare + select + add: ptxas turns the
             // two adds into VIADD, which B200 issues on whichever of the alu / fma pipes is free
             // (profiles/r1_int32_pipes.txt), so the saturated alu pipe loses one op per cell
-            // (measured +10 % on config 2)
+            // (measured +10 % on config 2)                                       (:31-32)
             asm("{ .reg .pred p;\n\t"
                 "setp.eq.s32 p, %1, %2;\n\t"
                 "add.s32 %0, %3, %4;\n\t"
@@ -150,14 +157,20 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
                 : "=r"(m2) : "r"(s.oc[k]), "r"(tch), "r"(dc), "r"(kp.miT), "r"(kp.maT));
         }
         // X[i][j] = max(M[i-1][j]+ox, X[i-1][j]+ex, Y[i-1][j]+ox)               (:83-88)
-        const int xraw = __viaddmax_s32(s.W[k], cx, s.Xh[k]);
+        const int xraw = __viaddmax_s32(FAST ? s.D[k] : s.W[k], cx, s.Xh[k]);
         const int xh = clean_tag_or(xraw, kTagX);
         // Y[i][j] = max(M[i][j-1]+oy, X[i][j-1]+oy, Y[i][j-1]+ey)               (:75-80)
         const int yraw = __viaddmax_s32(q, kp.oy, ypl);
         const int yc = clean_tag(yraw);
-        const int w  = max(yc, m2);                          // max(M, Y)
-        const int qn = __viaddmax_s32(xh, xe, m2);           // max(M, X)
-        const int dn = max(qn, yc);                          // max(M, X, Y)
+        int dn, qn;
+        if (FAST) {
+            dn = __vimax3_s32(m2, xh + xe, yc);              // max(M, X, Y)
+            qn = dn;
+        } else {
+            qn = __viaddmax_s32(xh, xe, m2);                 // max(M, X)
+            dn = max(qn, yc);                                // max(M, X, Y)
+            s.W[k] = max(yc, m2);                            // max(M, Y)
+        }
         // pointer byte = tagM + 4*tagX + 16*tagY with tag = raw - clean, accumulated four
         // cells per word by multiply-add (IMAD pipe); xraw - xh = tagX - 1, fixed below.
         const int sh = 1 << (8 * (k & 3));
@@ -166,7 +179,7 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
             if (k == kfin) { cap[0] = m2; cap[1] = xh + xe; cap[2] = yc; }
         }
         dul = s.D[k];
-        s.W[k] = w; s.Xh[k] = xh; s.D[k] = dn;
+        s.Xh[k] = xh; s.D[k] = dn;
         q = qn; ypl = EYZ ? yc : yc + kp.ey;
         if ((k & 3) == 3) { pw[k >> 2] = (unsigned)acc + 0x04040404u; acc = 0; }
     }
@@ -247,7 +260,7 @@ __device__ __forceinline__ int2 chain_fetch(const Chain &ch, int base, int n, in
 
 // One wavefront step of one pass.  GUARDED steps check whether the lane's row is inside
 // [1, n] (ramp-up / ramp-down) and capture the corner scores; steady steps do neither.
-template <int C, bool GUARDED, bool SUBST, bool EYZ, bool CHAINED>
+template <int C, bool GUARDED, bool SUBST, int VAR, bool CHAINED>
 __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KParams &kp,
                                           int n, int t, int lane, bool has_next,
                                           int fin_lane, int fin_k, int (&cap)[3], const Chain &ch)
@@ -277,13 +290,13 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
             ps.bnext = __ldcg(ps.bp);             // same address in every lane
         }
     }
-    const int dul_in = max(ps.q_prev, ps.y_prev); // D of (i-1, left neighbour column)
+    const int dul_in = (VAR >= 1) ? ps.q_prev : max(ps.q_prev, ps.y_prev);   // D of (i-1, left neighbour column)
     const int tch = ps.tnext;
     if (!GUARDED || (i >= 0 && i < n)) ps.tnext = (int)__ldg(ps.tp);     // row i+1 reads T[i]
     if (!GUARDED || (i >= 1 && i <= n)) {
         unsigned pw[C / 4];
         const int kfin = (GUARDED && i == n && lane == fin_lane) ? fin_k : -1;
-        strip_row<C, GUARDED, SUBST, EYZ>(s, kp, tch, ps.xe, ps.cx, q_in, y_in, dul_in,
+        strip_row<C, GUARDED, SUBST, VAR>(s, kp, tch, ps.xe, ps.cx, q_in, y_in, dul_in,
                                           ps.q_out, ps.y_out, pw, kfin, cap);
         store_ptr_words<C>(ps.pst, pw);
         if (has_next && lane == 31) {
@@ -308,7 +321,7 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
 //              bnd[i] with this pass's right edge 31 steps after lane 0 consumed it.
 //   ptr      : base of this pass's pointer bytes, laid out [step t][lane][C]
 //   fin_lane, fin_k : where column m lives in this pass (or fin_lane = -1)
-template <int C, bool SUBST, bool EYZ, bool CHAINED>
+template <int C, bool SUBST, int VAR, bool CHAINED>
 __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__restrict__ T,
                                           const uint8_t *__restrict__ O, int n, int m, int j0,
                                           bool has_next, const int2 *bnd, int2 *bnd_out,
@@ -360,14 +373,14 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     const int ramp_end = min(31, last_step);
     int t = 1;
     for (; t <= ramp_end; ++t)                    // ramp-up: lanes join one per step
-        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
+        pass_step<C, true, SUBST, VAR, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
     for (; t <= n - 1; ++t)                       // steady state: every lane on a row in [1, n-1]
-        pass_step<C, false, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
+        pass_step<C, false, SUBST, VAR, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
     for (; t <= last_step; ++t)                   // ramp-down: last row, lanes leave one per step
-        pass_step<C, true, SUBST, EYZ, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
+        pass_step<C, true, SUBST, VAR, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
 }
 
-template <bool SUBST, bool EYZ, bool CHAINED>
+template <bool SUBST, int VAR, bool CHAINED>
 __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const uint8_t *T,
                                               const uint8_t *O, int n, int m, int j0,
                                               bool has_next, const int2 *bnd, int2 *bnd_out,
@@ -377,7 +390,7 @@ __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const ui
 #define TANW_CASE(CC)                                                                              \
     case CC:                                                                                       \
         if constexpr (CC <= kMaxC)                                                                 \
-            fill_pass<CC, SUBST, EYZ, CHAINED>(kp, T, O, n, m, j0, has_next, bnd, bnd_out, ptr,     \
+            fill_pass<CC, SUBST, VAR, CHAINED>(kp, T, O, n, m, j0, has_next, bnd, bnd_out, ptr,     \
                                                fin_lane, fin_k, cap, ch);                           \
         break;
     switch (C) {
@@ -514,7 +527,7 @@ __device__ __forceinline__ int score_out(int v)
 #ifndef TANW_MINB
 #define TANW_MINB 4
 #endif
-template <bool SUBST, bool EYZ>
+template <bool SUBST, int VAR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
 {
@@ -557,7 +570,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
                 const int cc = m - 1 - j0;
                 const int fin_lane = last ? cc / C : -1;
                 const int fin_k = last ? cc % C : -1;
-                dispatch_pass<SUBST, EYZ, false>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
+                dispatch_pass<SUBST, VAR, false>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
                                                  ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap,
                                                  Chain{nullptr, nullptr, 0, false});
                 __syncwarp();
@@ -633,7 +646,7 @@ struct LineState {
     uint8_t *pst;
 };
 
-template <int C, bool GUARDED, bool SUBST, bool EYZ>
+template <int C, bool GUARDED, bool SUBST, int VAR>
 __device__ __forceinline__ void line_step(Strip<C> &s, LineState &ls, const KParams &kp, int n, bool act,
                                           int t, int gl, int fin_lane, int fin_k, int (&cap)[3])
 {
@@ -641,13 +654,13 @@ __device__ __forceinline__ void line_step(Strip<C> &s, LineState &ls, const KPar
     int q_in = __shfl_up_sync(kFull, ls.q_out, 1, kLineG);
     int y_in = __shfl_up_sync(kFull, ls.y_out, 1, kLineG);
     if (gl == 0) { q_in = ls.bq | kTagM; y_in = ls.bq; }        // column 0: M = Y = bg*i (:54-56)
-    const int dul_in = max(ls.q_prev, ls.y_prev);
+    const int dul_in = (VAR >= 1) ? ls.q_prev : max(ls.q_prev, ls.y_prev);
     const int tch = ls.tnext;
     if (!GUARDED || (i >= 0 && i < n)) ls.tnext = (int)__ldg(ls.tp);
     if (!GUARDED || (act && i >= 1 && i <= n)) {
         unsigned pw[C / 4];
         const int kfin = (GUARDED && i == n && gl == fin_lane) ? fin_k : -1;
-        strip_row<C, GUARDED, SUBST, EYZ>(s, kp, tch, ls.xe, ls.cx, q_in, y_in, dul_in,
+        strip_row<C, GUARDED, SUBST, VAR>(s, kp, tch, ls.xe, ls.cx, q_in, y_in, dul_in,
                                           ls.q_out, ls.y_out, pw, kfin, cap);
         store_ptr_words<C>(ls.pst, pw);
     }
@@ -712,7 +725,7 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
     return __shfl_sync(kFull, k, 0, kLineG);
 }
 
-template <int C, bool SUBST, bool EYZ>
+template <int C, bool SUBST, int VAR>
 __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, int p, uint8_t *ptr,
                                           unsigned *tile, int lane)
 {
@@ -768,11 +781,11 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
         const int last_step = nmax + kLineG - 1;
         int t = 1;
         for (; t <= min(kLineG - 1, last_step); ++t)         // ramp-up
-            line_step<C, true, SUBST, EYZ>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
+            line_step<C, true, SUBST, VAR>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
         for (; t <= nmin - 1; ++t)                           // every lane of every group on a row in [1, n-1]
-            line_step<C, false, SUBST, EYZ>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
+            line_step<C, false, SUBST, VAR>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
         for (; t <= last_step; ++t)                          // ramp-down and the taller pairs' tails
-            line_step<C, true, SUBST, EYZ>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
+            line_step<C, true, SUBST, VAR>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
         {   // the lane of the group that owns column m holds the corner scores
             const int src = (lane & ~(kLineG - 1)) + (act ? fin_lane : 0);
             const int v0 = __shfl_sync(kFull, cap[0], src);
@@ -808,7 +821,7 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
     }
 }
 
-template <bool SUBST, bool EYZ>
+template <bool SUBST, int VAR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
 {
@@ -828,10 +841,10 @@ align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
         const int p = (g == 0) ? quad.x : (g == 1) ? quad.y : (g == 2) ? quad.z : quad.w;
         const int C = line_c(a.pairs[quad.x].m);             // uniform: a quad holds one strip width
         switch (C) {
-        case 4:  line_quad<4,  SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
-        case 8:  line_quad<8,  SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
-        case 12: line_quad<12, SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
-        default: line_quad<16, SUBST, EYZ>(a, kp, p, ptr, tile, lane); break;
+        case 4:  line_quad<4,  SUBST, VAR>(a, kp, p, ptr, tile, lane); break;
+        case 8:  line_quad<8,  SUBST, VAR>(a, kp, p, ptr, tile, lane); break;
+        case 12: line_quad<12, SUBST, VAR>(a, kp, p, ptr, tile, lane); break;
+        default: line_quad<16, SUBST, VAR>(a, kp, p, ptr, tile, lane); break;
         }
         __syncwarp();
     }
@@ -855,7 +868,7 @@ struct LongArgs {
     int *scores;           // 3 ints
 };
 
-template <bool SUBST, bool EYZ>
+template <bool SUBST, int VAR>
 __global__ void __launch_bounds__(32, 8)
 align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
 {
@@ -878,7 +891,7 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
     ch.out = a.chain + (size_t)w * (size_t)a.chain_stride;
     ch.epoch = a.epoch;
     ch.first = (w == 0);
-    dispatch_pass<SUBST, EYZ, true>(C, kp, a.T, a.O, n, m, j0, !last, nullptr, nullptr,
+    dispatch_pass<SUBST, VAR, true>(C, kp, a.T, a.O, n, m, j0, !last, nullptr, nullptr,
                                     a.ptr + (size_t)w * (size_t)pass_bytes, fin_lane, fin_k, cap, ch);
     if (last && (int)(threadIdx.x & 31) == fin_lane && a.scores) {
         a.scores[0] = score_out(cap[0]);
