@@ -129,7 +129,7 @@ bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
     upd((int64_t)s->gap_open_y + s->gap_extend_y); upd(s->gap_extend_y);
     if (s->subst)
         for (int64_t i = 0; i < (int64_t)s->subst_k * s->subst_k; ++i) upd(s->subst[i]);
-    return (max_n_plus_m + 2) * pmax < (int64_t(1) << 25);
+    return (max_n_plus_m + 2) * pmax < (int64_t(1) << 22);
 }
 
 void fill_kparams(KParams &kp, const tanw_scoring *sc)
@@ -460,7 +460,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     }
     if (!scoring_in_range(sc, max_nm))
         return fail(ctx, TANW_E_RANGE,
-                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^25");
+                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^22");
     if (sc->subst) {
         int maxsym = 0;
         for (int64_t i = 0; i < symbols_len; ++i) maxsym = std::max<int>(maxsym, symbols[i]);
@@ -647,7 +647,7 @@ int tanw_batch_rescore(tanw_ctx *ctx, const tanw_scoring *sc)
         return fail(ctx, TANW_E_INVALID, "rescore needs a table of the same size (K = %d)", ctx->kp.subst_k);
     if (!scoring_in_range(sc, ctx->max_nm))
         return fail(ctx, TANW_E_RANGE,
-                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^25");
+                    "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^22");
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
     fill_kparams(ctx->kp, sc);
     ctx->opens_nonpositive = sc->gap_open_x <= 0 && sc->gap_open_y <= 0;

@@ -12,16 +12,16 @@
 //   * all H/E/F state (here M/X/Y) lives in registers: per column W = max(M,Y), X and
 //     D = max(M,X,Y) of the row above, per step the running Q = max(M,X) and Y of the column
 //     to the left;
-//   * scores are carried in int32 fixed point, value*4, and the low two bits hold the origin
+//   * scores are carried in int32 fixed point, value*64, and the low two bits hold the origin
 //     tag of a value (M = 2, X = 1, Y = 0).  A plain integer max over tagged candidates
 //     therefore returns the maximum AND, on equal values, the candidate that comes first in
 //     the reference's list order (M, X, Y) -- list.index(max(list)),
 //     textSeqCompare.py:72,:80,:88 -- without any compare/select for the argmax;
 //   * B200 issues integer min/max/logic on the "alu" pipe and IMAD on the "fma" pipe, 64
 //     lanes/clk/SM each (profiles/r1_int32_pipes.txt).  The recurrences need the alu pipe
-//     (VIADDMNMX, LOP3), so everything else is phrased as IMAD work: the three 2-bit
-//     traceback pointers of a cell are (raw max result) - (its cleaned value), and four
-//     cells' pointers are accumulated into one 32-bit word by multiply-add;
+//     (VIADDMNMX, LOP3), so everything else is phrased as IMAD work: scores are multiples of
+//     64 with the tag in bits 0-1, so the low six bits of dul + 4*xraw + 16*yraw ARE the three
+//     2-bit traceback pointers of the cell (two IMADs, no masking);
 //   * pointers are written one byte per cell, step-major, so every warp store is one
 //     contiguous 32*C byte segment;
 //   * the traceback runs in the same kernel right after the pair's fill: the warp prefetches
@@ -33,7 +33,7 @@
 
 namespace tanw {
 
-constexpr int      kShift   = 2;                 // fixed point: value << 2
+constexpr int      kShift   = 6;                 // fixed point: value << 6 (bits 2-5 stay zero)
 constexpr int      kTagM    = 2;                 // "came from M"
 constexpr int      kTagX    = 1;                 // "came from X"; "came from Y" is 0
 constexpr int      kTagMask = 3;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
     int q = q_in;                             // general: Q of the cell to the left; FAST: its D
     int ypl = EYZ ? y_in : y_in + kp.ey;      // Y of the column to the left, + ey
     int dul = dul_in;
-    int acc = 0;
+    unsigned bytes[4];
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         // M[i][j] = max(M,X,Y)[i-1][j-1] + score, tagged as an M value         (:70-72)
@@ -171,17 +171,24 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
             dn = max(qn, yc);                                // max(M, X, Y)
             s.W[k] = max(yc, m2);                            // max(M, Y)
         }
-        // pointer byte = tagM + 4*tagX + 16*tagY with tag = raw - clean, accumulated four
-        // cells per word by multiply-add (IMAD pipe); xraw - xh = tagX - 1, fixed below.
-        const int sh = 1 << (8 * (k & 3));
-        acc += (dul - dc) * sh + (xraw - xh) * (4 * sh) + (yraw - yc) * (16 * sh);
+        // pointer byte: scores are multiples of 64, so the low six bits of
+        // dul + 4*xraw + 16*yraw are exactly tagM | tagX<<2 | tagY<<4 (two IMADs); bits 6-7 are
+        // value garbage that the traceback masks off.
+        int rb;
+        asm("mad.lo.s32 %0, %1, 4, %2;" : "=r"(rb) : "r"(xraw), "r"(dul));
+        asm("mad.lo.s32 %0, %1, 16, %0;" : "+r"(rb) : "r"(yraw));
+        bytes[k & 3] = (unsigned)rb;
         if (FINAL) {
             if (k == kfin) { cap[0] = m2; cap[1] = xh + xe; cap[2] = yc; }
         }
         dul = s.D[k];
         s.Xh[k] = xh; s.D[k] = dn;
         q = qn; ypl = EYZ ? yc : yc + kp.ey;
-        if ((k & 3) == 3) { pw[k >> 2] = (unsigned)acc + 0x04040404u; acc = 0; }
+        if ((k & 3) == 3) {
+            const unsigned lo = __byte_perm(bytes[0], bytes[1], 0x0040);
+            const unsigned hi = __byte_perm(bytes[2], bytes[3], 0x0040);
+            pw[k >> 2] = __byte_perm(lo, hi, 0x5410);
+        }
     }
     q_out = q;
     y_out = EYZ ? ypl : ypl - kp.ey;
