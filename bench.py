@@ -40,6 +40,24 @@ DEFAULT_PARAMS = (8, -4, -7, -7, -3, 0, -1)
 NOMINAL_INT32_PEAK = 148 * 64 * 1.965e9     # alu pipe, lane-ops/s
 
 
+def ncu_traffic(workload, npairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed ncu --set full summary of the same workload (profiles/); None if it does not apply."""
+    if workload != 'c2' or npairs != WORKLOADS['c2']['default_pairs']:
+        return None
+    path = os.path.join(ROOT, 'profiles', 'r1e_align_pairs_ncu.txt')
+    scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+    total = 0.0
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                total += float(f[2]) * scale.get(f[1], 1.0)
+    except (OSError, ValueError):
+        return None
+    return total or None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -403,7 +421,7 @@ def main():
                      breakdown_ms=dict(h2d=tm['h2d_ms'], kernel=tm['kernel_ms'], d2h=tm['d2h_ms'])),
             gpu_launches=launches,
             roofline=dict(bound='alu', achieved=ach_ops / 1e12, peak=int32_peak / 1e12, unit='Tlane-op/s',
-                          frac=ach_ops / int32_peak, traffic=None,
+                          frac=ach_ops / int32_peak, traffic=ncu_traffic(args.workload, npairs),
                           note='achieved = %d algorithmic int32 ops/cell (SURVEY 8(d)) x cells / launch time; '
                                'peak = measured dependency-free add.s32 / max.s32 issue rate on all SMs '
                                '(tanw_measure_int32_peak); nominal alu-pipe figure of SURVEY 8(d) is %.1f'
