@@ -55,3 +55,18 @@ def test_no_cpu_fallback_without_device():
     from text_alignment_b200 import textSeqCompare as tsc
     with pytest.raises(_native.NativeError):
         tsc.perform_alignment(list('abc'), list('abd'))
+
+
+def test_null_context_is_an_error_not_a_crash():
+    import ctypes
+    lib = _native.load()
+    assert lib.tanw_batch_run(None) == 1                      # TANW_E_INVALID
+    assert lib.tanw_sync(None) == 1
+    assert lib.tanw_destroy(None) == 0
+    assert lib.tanw_set_arena_limit(None, 0) == 1
+    t = _native.Timing()
+    assert lib.tanw_last_timing(None, ctypes.byref(t)) == 1
+    assert b'NULL' in lib.tanw_last_error(None)
+    h = ctypes.c_void_p()
+    rc = lib.tanw_create(10 ** 6, ctypes.byref(h))            # no such device anywhere
+    assert rc == 4 and not h.value                            # TANW_E_NODEVICE

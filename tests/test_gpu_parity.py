@@ -400,3 +400,69 @@ def test_c2_all_10k_pages_bit_exact(tsc, oracle):
 def test_c4_256_pages_bit_exact(tsc, oracle):
     pairs = [synth.c4_pair(100 + k) for k in range(256)]
     _check_packed_vs_oracle(tsc, oracle, pairs, threads=16)
+
+
+# ---- C-ABI error behaviour (int status + last_error, no aborts) ------------------
+
+def test_abi_argument_errors(tsc):
+    import ctypes
+    from text_alignment_b200 import _native
+    ctx = _native.Context(0)
+    try:
+        lib, h = ctx._lib, ctx._h
+        sc, _ = ctx.make_scoring(*DEFAULT)
+        assert lib.tanw_batch_run(h) == 6                                     # TANW_E_STATE
+        assert b'before tanw_batch_prepare' in lib.tanw_last_error(h)
+        buf = np.frombuffer(b'abcabd', dtype=np.uint8)
+        good = dict(t_off=np.array([0], np.int64), n=np.array([3], np.int32),
+                    o_off=np.array([3], np.int64), m=np.array([3], np.int32))
+        with pytest.raises(ValueError):                                        # offsets outside the buffer
+            ctx.align_batch(buf, good['t_off'], good['n'], np.array([5], np.int64), good['m'], (sc, None))
+        with pytest.raises(ValueError):                                        # negative length
+            ctx.align_batch(buf, good['t_off'], np.array([-1], np.int32), good['o_off'], good['m'], (sc, None))
+        with pytest.raises(ValueError):                                        # table arrays differ in length
+            ctx.align_batch(buf, good['t_off'], np.array([3, 3], np.int32), good['o_off'], good['m'], (sc, None))
+        tab = np.zeros((2, 2), np.int32)                                       # symbol codes >= K
+        with pytest.raises(ValueError):
+            ctx.align_batch(buf, good['t_off'], good['n'], good['o_off'], good['m'],
+                            ctx.make_scoring(0, 0, -1, -1, -1, -1, -1, subst=tab))
+        # op buffer too small: the library refuses instead of writing out of bounds
+        ctx.prepare(buf, good['t_off'], good['n'], good['o_off'], good['m'], (sc, None))
+        ctx.run()
+        ops = np.zeros(2, np.uint8); off = np.zeros(1, np.int64); ln = np.zeros(1, np.int32)
+        u8p, i64p, i32p = (ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32))
+        rc = lib.tanw_batch_fetch(h, ops.ctypes.data_as(u8p), off.ctypes.data_as(i64p), 2, ln.ctypes.data_as(i32p), None)
+        assert rc == 1 and b'op buffer too small' in lib.tanw_last_error(h)
+        # a non-canonical op layout is honoured
+        ops = np.full(40, 9, np.uint8); off = np.array([17], np.int64)
+        rc = lib.tanw_batch_fetch(h, ops.ctypes.data_as(u8p), off.ctypes.data_as(i64p), 40, ln.ctypes.data_as(i32p), None)
+        assert rc == 0 and ln[0] == 3 and ops[17:20].tolist() == [0, 0, 0] and ops[16] == 9 and ops[20] == 9
+        # and the context still works afterwards
+        out = ctx.align_batch(buf, good['t_off'], good['n'], good['o_off'], good['m'], (sc, None))
+        assert out[0][:3].tolist() == [0, 0, 0]
+    finally:
+        ctx.close()
+
+
+def test_empty_batch(tsc):
+    z64, z32 = np.zeros(0, np.int64), np.zeros(0, np.int32)
+    ops, off, ln, sc = tsc.align_packed(np.zeros(0, np.uint8), z64, z32, z64, z32, DEFAULT)
+    assert ln.size == 0 and sc.shape == (0, 3)
+    assert tsc.perform_alignment_batch([]) == []
+
+
+def test_plain_c_caller(tmp_path):
+    """examples/abi_example.c: the C ABI is usable without Python (SURVEY App. B KATs)."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which('gcc'):
+        pytest.skip('no gcc')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'abi_example')
+    libdir = os.path.join(root, 'text_alignment_b200')
+    subprocess.check_call(['gcc', '-I' + os.path.join(root, 'include'), os.path.join(root, 'examples', 'abi_example.c'),
+                           '-o', exe, '-L' + libdir, '-ltanw', '-Wl,-rpath,' + libdir])
+    out = subprocess.check_output([exe], text=True).splitlines()
+    assert out == ['domi_nus', '____dns_', '(M, X, Y)[n][m] = (2, -10, -7)',
+                   'allel_____u__ia', 'a l l e l u y a', '(M, X, Y)[n][m] = (14, -3, 2)']
