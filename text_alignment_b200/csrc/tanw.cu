@@ -119,7 +119,7 @@ bool device_is_blackwell(int device, cudaDeviceProp *prop_out)
 }
 
 // int32 fixed point: every finite intermediate must stay far away from kNeg = -2^30.
-// |value| <= (n+m+2) * max|param| ; carried << 2 and offset by up to ex*n once more.
+// |value| <= (n+m+2) * max|param| ; carried << 6 and offset by up to ex*n once more: 2^22 * 2 * 64 = 2^29 < 2^30.
 bool scoring_in_range(const tanw_scoring *s, int64_t max_n_plus_m)
 {
     int64_t pmax = 1;

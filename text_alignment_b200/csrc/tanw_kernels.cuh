@@ -9,9 +9,9 @@
 //     the C-column strip [j0 + l*C, j0 + (l+1)*C) and walks down the transcript rows, one row
 //     per step, skewed by one step per lane (anti-diagonal wavefront).  The strip's right-edge
 //     values travel to lane l+1 with two __shfl_up_sync per step;
-//   * all H/E/F state (here M/X/Y) lives in registers: per column W = max(M,Y), X and
-//     D = max(M,X,Y) of the row above, per step the running Q = max(M,X) and Y of the column
-//     to the left;
+//   * all H/E/F state (here M/X/Y) lives in registers: per column X and D = max(M,X,Y) of the
+//     row above (plus W = max(M,Y) in the general variant), per step the running D (or
+//     Q = max(M,X)) and Y of the column to the left;
 //   * scores are carried in int32 fixed point, value*64, and the low two bits hold the origin
 //     tag of a value (M = 2, X = 1, Y = 0).  A plain integer max over tagged candidates
 //     therefore returns the maximum AND, on equal values, the candidate that comes first in
@@ -25,8 +25,11 @@
 //   * pointers are written one byte per cell, step-major, so every warp store is one
 //     contiguous 32*C byte segment;
 //   * the traceback runs in the same kernel right after the pair's fill: the warp prefetches
-//     a 32x32 tile of pointer bytes around the current cell into shared memory with 32
-//     independent loads per lane, one lane walks inside the tile, repeat.
+//     a 64x64 tile of pointer bytes whose corner is the current cell into shared memory with
+//     32 independent word loads per lane, one lane walks inside the tile (branch-free), repeat;
+//   * short pairs (m <= 128) are aligned four per warp, 8 lanes each (align_lines_kernel); one
+//     whole-manuscript pair is spread over one warp per column stripe, all resident at once,
+//     handing their edges over through flag-stamped records (align_long_kernel).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,11 +50,11 @@ constexpr int      kWarpsPerBlock = 4;
 constexpr unsigned kFull    = 0xFFFFFFFFu;
 
 struct KParams {
-    int maT, miT;            // (match<<2)|kTagM, (mismatch<<2)|kTagM
-    int ox, ex, oy, ey;      // (gox+gex)<<2, gex<<2, (goy+gey)<<2, gey<<2
-    int bg;                  // boundary_gap<<2 (module-level gap_extend, textSeqCompare.py:9)
+    int maT, miT;            // (match<<6)|kTagM, (mismatch<<6)|kTagM
+    int ox, ex, oy, ey;      // (gox+gex)<<6, gex<<6, (goy+gey)<<6, gey<<6
+    int bg;                  // boundary_gap<<6 (module-level gap_extend, textSeqCompare.py:9)
     int subst_k;
-    const int *subst;        // device table, entry = (score<<2)|kTagM, or nullptr
+    const int *subst;        // device table, entry = (score<<6)|kTagM, or nullptr
 };
 
 struct PairDesc {
