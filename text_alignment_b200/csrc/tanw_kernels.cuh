@@ -227,7 +227,8 @@ struct PassState {
     const int2 *bp;        // &bnd[t+2]: next boundary row to prefetch
     int2 *bw;              // &bnd[i+1]: where lane 31 leaves its right edge next
     uint8_t *pst;          // pointer bytes of this lane for the next step
-    int2 blk_cur, blk_next; // chained passes: 8-row blocks of the left boundary, one row per lane 0..7
+    int2 blk_cur;          // chained passes: current 8-row block of the left boundary, one row per lane 0..7
+    int4 blk_raw;          // chained passes: the next block as loaded (stamps not yet checked)
 };
 
 // Chained passes (one huge pair spread over many warps): stripe w leaves its right edge in
@@ -256,14 +257,21 @@ __device__ __forceinline__ void st_volatile_v4(int4 *p, int4 v)
     asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// Rows base .. base+7 of the left stripe's edge, one per lane 0..7 (spins until they are there).
-__device__ __forceinline__ int2 chain_fetch(const Chain &ch, int base, int n, int lane)
+// Rows base .. base+7 of the left stripe's edge, one per lane 0..7.  chain_issue only starts the
+// load; chain_take, called a block (8 steps) later, checks the stamps and spins only if the
+// producer has not got there yet -- so the L2 round trip overlaps the 8 steps in between
+// (ncu: with a blocking fetch a stripe spent a third of its time in this load).
+__device__ __forceinline__ int4 chain_issue(const Chain &ch, int base, int n, int lane)
 {
     int4 v = make_int4(0, ch.epoch, 0, ch.epoch);
+    if (lane < kChainBlock && base + lane <= n) v = ld_volatile_v4(ch.in + base + lane);
+    return v;
+}
+__device__ __forceinline__ int2 chain_take(const Chain &ch, int4 v, int base, int n, int lane)
+{
     const bool mine = lane < kChainBlock && base + lane <= n;
-    for (;;) {
+    while (!__all_sync(kFull, v.y == ch.epoch && v.w == ch.epoch)) {
         if (mine) v = ld_volatile_v4(ch.in + base + lane);
-        if (__all_sync(kFull, v.y == ch.epoch && v.w == ch.epoch)) break;
     }
     return make_int2(v.x, v.z);
 }
@@ -289,9 +297,9 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
                 ps.bnext = make_int2((kp.bg * r) | kTagM, kp.bg * r);       // column 0 (:54-56)
             } else {
                 const int j = (r - 1) & (kChainBlock - 1);
-                if (j == 0) {
-                    ps.blk_cur = ps.blk_next;
-                    if (r + kChainBlock <= n) ps.blk_next = chain_fetch(ch, r + kChainBlock, n, lane);
+                if (j == 0) {                     // rows r .. r+7 were requested 8 steps ago
+                    ps.blk_cur = chain_take(ch, ps.blk_raw, r, n, lane);
+                    if (r + kChainBlock <= n) ps.blk_raw = chain_issue(ch, r + kChainBlock, n, lane);
                 }
                 ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, j);
                 ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, j);
@@ -358,13 +366,13 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     ps.q_prev = (kp.bg * c0) | kTagM;             // left neighbour column, row 0
     ps.y_prev = kNeg;                             // (Y[0][j] = -inf, also at j = 0)
     ps.blk_cur = make_int2(0, 0);
-    ps.blk_next = make_int2(0, 0);
+    ps.blk_raw = make_int4(0, 0, 0, 0);
     if (CHAINED) {
         if (ch.first) {
             ps.bnext = make_int2(kp.bg | kTagM, kp.bg);                     // row 1 of column 0
         } else {
-            ps.blk_cur = chain_fetch(ch, 1, n, lane);                       // rows 1..8
-            if (1 + kChainBlock <= n) ps.blk_next = chain_fetch(ch, 1 + kChainBlock, n, lane);
+            ps.blk_cur = chain_take(ch, chain_issue(ch, 1, n, lane), 1, n, lane);       // rows 1..8
+            if (1 + kChainBlock <= n) ps.blk_raw = chain_issue(ch, 1 + kChainBlock, n, lane);
             ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, 0);
             ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, 0);
         }
