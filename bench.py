@@ -34,6 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = 'batched affine-NW GCUPS'      # BASELINE.json metric; pages/sec is reported beside it as pages_per_s
 OPS_PER_CELL = 21          # algorithmic int32 ops per cell of the reference recurrence
 PTR_BYTES_PER_CELL = 1     # three 2-bit pointers packed in one byte
 DEFAULT_PARAMS = (8, -4, -7, -7, -3, 0, -1)
@@ -246,7 +247,7 @@ def run_reference(args):
     desc = ('%d crops of %s pages per step (first ~%dx%d chars of seeds 2000000..), one per host core, '
             'pure-Python restatement of textSeqCompare.py (oracle/py_port.py); the reference is Python and '
             'cannot travel to the GPU box' % (len(sample), args.workload, len(sample[0][0]), len(sample[0][1])))
-    line = dict(impl='reference', metric='affine_nw_gcups', value=gcups, unit='GCUPS', n_gpus=args.gpus,
+    line = dict(impl='reference', metric=METRIC, value=gcups, unit='GCUPS', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=wall / max(args.steps, 1) * 1e3,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64 (python float)', data='synthetic',
                 config=dict(workload=wl['name'], scoring=list(DEFAULT_PARAMS[:6])),
@@ -443,7 +444,7 @@ def main():
         ach_ops = cells * OPS_PER_CELL / launch_s
         ach_gbs = cells * PTR_BYTES_PER_CELL / launch_s / 1e9
         line = dict(
-            metric='affine_nw_gcups', value=gcups, unit='GCUPS', n_gpus=world, steps=args.steps,
+            metric=METRIC, value=gcups, unit='GCUPS', n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='weak',
             vs_baseline=None, dtype='int32', data='synthetic',
             config=dict(workload=wl['name'], pairs_per_gpu=npairs, cells_per_gpu=cells,
