@@ -466,3 +466,21 @@ def test_plain_c_caller(tmp_path):
     out = subprocess.check_output([exe], text=True).splitlines()
     assert out == ['domi_nus', '____dns_', '(M, X, Y)[n][m] = (2, -10, -7)',
                    'allel_____u__ia', 'a l l e l u y a', '(M, X, Y)[n][m] = (14, -3, 2)']
+
+
+def test_small_arena_limit_reduces_occupancy_not_correctness(oracle):
+    """The pointer arena is per resident warp; a tight limit must only reduce the number of
+    resident warps (or refuse a pair that cannot fit at all), never change results."""
+    from text_alignment_b200 import _native
+    ctx = _native.Context(0)
+    try:
+        pairs = [synth.c2_pair(300 + k) for k in range(12)] + [synth.c3_pair(k) for k in range(40)]
+        ctx.set_arena_limit(24 << 20)                     # room for ~2 CTAs of page slots
+        _check_ctx_vs_oracle(ctx, oracle, pairs)
+        ctx.set_arena_limit(1 << 20)                      # smaller than one page slot
+        with pytest.raises(MemoryError):
+            ctx.align_batch(*_pack(pairs[:2]), ctx.make_scoring(*DEFAULT))
+        ctx.set_arena_limit(0)                            # back to the default
+        _check_ctx_vs_oracle(ctx, oracle, pairs[:3])
+    finally:
+        ctx.close()
