@@ -425,6 +425,20 @@ def main():
     ctx_b.close()
     clocks = sampler.stop(w0, y1)
 
+    # ---- the Python list <-> buffer shim, reported separately (it is not the path) ----
+    shim = None
+    if rank == 0 and args.workload in ('c2', 'c4', 'c1'):
+        from text_alignment_b200 import textSeqCompare as tsc_mod
+        k = min(256, npairs)
+        lists = [(list(t), list(o)) for t, o in pairs[:k]]
+        tsc_mod.perform_alignment_batch(lists[:8], devices=[local_rank])
+        s0 = time.perf_counter()
+        tsc_mod.perform_alignment_batch(lists, devices=[local_rank])
+        s1 = time.perf_counter()
+        shim = dict(pages=k, ms_per_page=(s1 - s0) * 1e3 / k, pages_per_s=k / (s1 - s0),
+                    what='perform_alignment_batch on Python lists: interning to uint8 codes, one launch, '
+                         'op strings back to two lists per page')
+
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s * 1e3, w1 - w0, pipe_s * 1e3], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -473,6 +487,8 @@ def main():
                           hbm=dict(bound='hbm', achieved=ach_gbs, peak=hbm_peak, unit='GB/s',
                                    frac=ach_gbs / hbm_peak, peak_source=hbm_src)),
             clocks=clocks)
+        if shim:
+            line['python_list_shim'] = shim
         if not args.no_cpu_baseline:
             t_s = 12.0
             c_cells, c_wall, sample = cpu_python_port(pairs, cores, t_s)
