@@ -508,23 +508,29 @@ __device__ __forceinline__ int traceback_warp(const uint8_t *ptr, int n, int m, 
             }
             __syncwarp();
             // ---- walk inside the tile -----------------------------------------------------
+            // state 0: diagonal, next = mat_ptr; 1: x-gap, next = x_mat_ptr; 2: y-gap, next =
+            // y_mat_ptr (:115-145).  One lane, a chain of dependent shared-memory loads: the loop
+            // keeps only  load -> shift -> mask -> subtract  on that chain (byte-addressed tile,
+            // running offset, exit counters that do not depend on the loaded byte).
             if (lane == 0) {
-                const int col_lo = (wq_hi - (kTileWords - 1)) * 4;      // 0-based column of tile word 0
-                int r = 0;
-                while (r < kTileRows && x > 0 && y > 0) {
-                    const int cw = (y - 1) - col_lo;
-                    if (cw < 0) break;
-                    const unsigned b = (tile[r * kTileStride + (cw >> 2)] >> (8 * (cw & 3))) & 0xFFu;
-                    if (st < 0) st = 2 - (int)(b & 3u);                               // :102
-                    // state 0: diagonal, next = mat_ptr; 1: x-gap, next = x_mat_ptr; 2: y-gap,
-                    // next = y_mat_ptr (:115-145) -- branch-free: the chain of dependent
-                    // instructions per path step is what bounds a whole-manuscript traceback
+                const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
+                const int col_lo = (wq_hi - (kTileWords - 1)) * 4;      // 0-based column of tile byte 0
+                int off = (y - 1) - col_lo;                             // row 0 of the tile, 60..63
+                if (st < 0) st = 2 - (int)(tb[off] & 3u);                             // :102
+                const int xr0 = min(x, kTileRows), yr0 = min(y, off + 1);
+                int xr = xr0, yr = yr0;                                 // row / column moves left here
+                while (xr > 0 && yr > 0) {
+                    const unsigned b = tb[off];
                     const int dx = (st != 2), dy = (st != 1);
                     ++k;
                     *(ops_end - k) = (uint8_t)st;
+                    off += dx * (kTileStride * 4) - dy;
+                    xr -= dx;
+                    yr -= dy;
                     st = 2 - (int)((b >> (2 * st)) & 3u);
-                    x -= dx; r += dx; y -= dy;
                 }
+                x -= xr0 - xr;
+                y -= yr0 - yr;
             }
             x = __shfl_sync(kFull, x, 0);
             y = __shfl_sync(kFull, y, 0);
