@@ -725,19 +725,24 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
         for (int q = 0; q < 2 * C / 4; ++q) tile[gl * kLineTile + q] = w[q];
         __syncwarp();
         if (mine && gl == 0) {
+            const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
             const int col0 = (sidx - 1) * C;                 // 0-based column of the window start
-            int r = 0;
-            while (r < kLineG && x > 0 && y > 0) {
-                const int cw = (y - 1) - col0;
-                if (cw < 0) break;
-                const unsigned b = (tile[r * kLineTile + (cw >> 2)] >> (8 * (cw & 3))) & 0xFFu;
-                if (st < 0) st = 2 - (int)(b & 3u);                                   // :102
-                const int dx = (st != 2), dy = (st != 1);                             // :115-145
+            int off = (y - 1) - col0;                        // row 0 of the window, C .. 2C-1
+            if (st < 0) st = 2 - (int)(tb[off] & 3u);                                 // :102
+            const int xr0 = min(x, kLineG), yr0 = min(y, off + 1);
+            int xr = xr0, yr = yr0;
+            while (xr > 0 && yr > 0) {                                                // :115-145
+                const unsigned b = tb[off];
+                const int dx = (st != 2), dy = (st != 1);
                 ++k;
                 *(ops_end - k) = (uint8_t)st;
+                off += dx * (kLineTile * 4) - dy;
+                xr -= dx;
+                yr -= dy;
                 st = 2 - (int)((b >> (2 * st)) & 3u);
-                x -= dx; r += dx; y -= dy;
             }
+            x -= xr0 - xr;
+            y -= yr0 - yr;
         }
         x = __shfl_sync(kFull, x, 0, kLineG);
         y = __shfl_sync(kFull, y, 0, kLineG);
