@@ -23,6 +23,26 @@ namespace {
 
 thread_local std::string g_last_error;   // for failures that have no context yet
 
+// Page-locked host vectors: the pair / order / quad tables are rebuilt for every batch and
+// uploaded with cudaMemcpyAsync, which is only asynchronous (and only reaches full PCIe speed)
+// from pinned memory.  Capacity is kept across batches, so the allocation cost is paid once.
+template <class T>
+struct PinnedAlloc {
+    typedef T value_type;
+    PinnedAlloc() = default;
+    template <class U> PinnedAlloc(const PinnedAlloc<U> &) {}
+    T *allocate(size_t n)
+    {
+        void *p = nullptr;
+        if (cudaMallocHost(&p, n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+        return static_cast<T *>(p);
+    }
+    void deallocate(T *p, size_t) { cudaFreeHost(p); }
+    template <class U> bool operator==(const PinnedAlloc<U> &) const { return true; }
+    template <class U> bool operator!=(const PinnedAlloc<U> &) const { return false; }
+};
+template <class T> using pinned_vector = std::vector<T, PinnedAlloc<T>>;
+
 struct HostTimer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     float ms() const
@@ -62,7 +82,7 @@ struct tanw_ctx {
 
     DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_prog, d_quads;
     std::vector<int> h_line;              // pairs routed to the four-per-warp line kernel
-    std::vector<int4> h_quads;
+    pinned_vector<int4> h_quads;
     LineArgs largs;
     int line_grid = 0, occ_line = 0;
     bool use_lines = true;
@@ -71,8 +91,8 @@ struct tanw_ctx {
     int long_epoch = 0;                   // stamps the chain records of a launch
     DevBuf d_chain;
     int64_t long_cells = int64_t(1) << 26;   // pairs with n*m >= this use the chained-pass path
-    std::vector<PairDesc> h_pairs;
-    std::vector<int> h_order;
+    pinned_vector<PairDesc> h_pairs;
+    pinned_vector<int> h_order, h_order_sorted;
     std::vector<int64_t> h_ops_off;       // canonical device layout: prefix sums of n+m
     std::vector<uint8_t> h_stage;         // used when the caller's op layout is not canonical
 
@@ -438,7 +458,6 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         ctx->h_ops_off[(size_t)p] = ops_total;
         ops_total += np + mp;
         cells += np * mp;
-        const int64_t pb = ptr_bytes((int)np, (int)mp);
         ptr_total += np * mp;
         max_nm = std::max(max_nm, np + mp);
         // a batch of one or two pages (the drop-in single call) would occupy one or two warps:
@@ -457,7 +476,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
             ctx->h_line.push_back((int)p);
             max_line_slot = std::max<int64_t>(max_line_slot, line_ptr_bytes((int)np, (int)mp));
         } else {
-            max_slot = std::max(max_slot, pb);
+            max_slot = std::max<int64_t>(max_slot, ptr_bytes((int)np, (int)mp));
             max_n = std::max(max_n, (int)np);
         }
     }
@@ -486,25 +505,31 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
     ctx->h_quads.clear();
     if (!ctx->h_line.empty()) {
         // counting sort on (strip-width class, n) descending; pairs without cells sort last
-        const std::vector<PairDesc> &hp = ctx->h_pairs;
+        const pinned_vector<PairDesc> &hp = ctx->h_pairs;
         const int NK = 4 * (kLineMaxN + 1);
-        auto key_of = [&hp](int p) {
-            const PairDesc &d = hp[(size_t)p];
+        const size_t nl = ctx->h_line.size();
+        std::vector<int> key(nl);                 // descending (class, n) -> ascending bucket
+        for (size_t i = 0; i < nl; ++i) {
+            const PairDesc &d = hp[(size_t)ctx->h_line[i]];
             const bool act = d.n > 0 && d.m > 0;
-            const int cls = act ? line_c(d.m) / 4 - 1 : 0;
-            return cls * (kLineMaxN + 1) + (act ? d.n : 0);
-        };
+            key[i] = NK - 1 - ((act ? line_c(d.m) / 4 - 1 : 0) * (kLineMaxN + 1) + (act ? d.n : 0));
+        }
         std::vector<int> count((size_t)NK + 1, 0);
-        for (int p : ctx->h_line) ++count[(size_t)(NK - 1 - key_of(p)) + 1];
+        for (size_t i = 0; i < nl; ++i) ++count[(size_t)key[i] + 1];
         for (int b = 1; b <= NK; ++b) count[(size_t)b] += count[(size_t)b - 1];
-        std::vector<int> sorted(ctx->h_line.size());
-        for (int p : ctx->h_line) sorted[(size_t)count[(size_t)(NK - 1 - key_of(p))]++] = p;
+        std::vector<int> sorted(nl), skey(nl);
+        for (size_t i = 0; i < nl; ++i) {
+            const int at = count[(size_t)key[i]]++;
+            sorted[(size_t)at] = ctx->h_line[i];
+            skey[(size_t)at] = key[i];
+        }
+        ctx->h_quads.reserve(nl / 4 + 8);
         size_t i = 0;
-        while (i < sorted.size()) {
-            const int cls = key_of(sorted[i]) / (kLineMaxN + 1);
+        while (i < nl) {
+            const int cls = (NK - 1 - skey[i]) / (kLineMaxN + 1);
             int q[4] = { -1, -1, -1, -1 };
             int c = 0;
-            while (c < 4 && i < sorted.size() && key_of(sorted[i]) / (kLineMaxN + 1) == cls) q[c++] = sorted[i++];
+            while (c < 4 && i < nl && (NK - 1 - skey[i]) / (kLineMaxN + 1) == cls) q[c++] = sorted[i++];
             ctx->h_quads.push_back(make_int4(q[0], q[1], q[2], q[3]));
         }
     }
@@ -514,7 +539,7 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
         // Largest pairs first (greedy longest-processing-time) only needs an approximate order:
         // one stable counting sort on n*m quantised to 16 bits, O(pairs), instead of a
         // comparison sort (which cost 8 ms of host time per 125k line pairs).
-        const std::vector<PairDesc> &hp = ctx->h_pairs;
+        const pinned_vector<PairDesc> &hp = ctx->h_pairs;
         int64_t max_cells = 1;
         for (int p : ctx->h_order) max_cells = std::max(max_cells, (int64_t)hp[(size_t)p].n * hp[(size_t)p].m);
         int shift = 0;
@@ -525,7 +550,8 @@ int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_le
             ++count[(size_t)(65535 - (c >> shift)) + 1];
         }
         for (size_t b = 1; b <= 65536; ++b) count[b] += count[b - 1];
-        std::vector<int> sorted((size_t)n_batch);
+        pinned_vector<int> &sorted = ctx->h_order_sorted;
+        sorted.resize((size_t)n_batch);
         for (int p : ctx->h_order) {
             const int64_t c = (int64_t)hp[(size_t)p].n * hp[(size_t)p].m;
             sorted[(size_t)count[(size_t)(65535 - (c >> shift))]++] = p;
