@@ -412,9 +412,27 @@ int tanw_sync(tanw_ctx *ctx)
     return TANW_OK;
 }
 
+static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_len,
+                        const int64_t *t_off, const int32_t *n, const int64_t *o_off,
+                        const int32_t *m, int64_t n_pairs, const tanw_scoring *sc);
+
+// No exception may cross the C ABI: host allocations (std::vector, pinned tables) can throw.
 int tanw_batch_prepare(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_len,
                        const int64_t *t_off, const int32_t *n, const int64_t *o_off,
                        const int32_t *m, int64_t n_pairs, const tanw_scoring *sc)
+{
+    try {
+        return prepare_impl(ctx, symbols, symbols_len, t_off, n, o_off, m, n_pairs, sc);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, TANW_E_NOMEM, "out of host memory while building the batch tables");
+    } catch (...) {
+        return fail(ctx, TANW_E_INVALID, "unexpected exception in tanw_batch_prepare");
+    }
+}
+
+static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_len,
+                        const int64_t *t_off, const int32_t *n, const int64_t *o_off,
+                        const int32_t *m, int64_t n_pairs, const tanw_scoring *sc)
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     HostTimer host_timer;
@@ -681,8 +699,12 @@ int tanw_batch_rescore(tanw_ctx *ctx, const tanw_scoring *sc)
     fill_kparams(ctx->kp, sc);
     ctx->opens_nonpositive = sc->gap_open_x <= 0 && sc->gap_open_y <= 0;
     if (sc->subst) {
-        int rc = upload_subst(ctx, sc, nullptr);
-        if (rc) return rc;
+        try {
+            int rc = upload_subst(ctx, sc, nullptr);
+            if (rc) return rc;
+        } catch (const std::bad_alloc &) {
+            return fail(ctx, TANW_E_NOMEM, "out of host memory for the substitution table");
+        }
     }
     ctx->ran = false;
     return TANW_OK;
@@ -755,7 +777,11 @@ int tanw_batch_fetch(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_
     int64_t d2h = 0;
     uint8_t *dst = ops;
     if (!canonical) {
-        ctx->h_stage.resize((size_t)ctx->ops_total);
+        try {
+            ctx->h_stage.resize((size_t)ctx->ops_total);
+        } catch (const std::bad_alloc &) {
+            return fail(ctx, TANW_E_NOMEM, "out of host memory for the op staging buffer");
+        }
         dst = ctx->h_stage.data();
     }
     if (ctx->ops_total > 0) {
