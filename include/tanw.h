@@ -108,6 +108,13 @@ int  tanw_set_arena_limit(tanw_ctx *ctx, int64_t bytes);
  * (BASELINE config 5, 100k x 80k) uses the whole GPU.  Default 2^26.  Results are identical
  * on both paths; the threshold only moves work between them. */
 int  tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells);
+/* A chained-pass pair whose traceback pointers (1 byte per cell) exceed the arena limit is cut
+ * into bands of rows: one forward fill that keeps only the per-column state at every band edge,
+ * then, bottom band first, a second fill of each band that stores its pointers and the
+ * traceback through it (about twice the fill work, memory bounded by one band).  Pages too large
+ * for one warp's share of the arena take the same route.  rows > 0 forces bands of that height
+ * (tests; tuning), 0 = only when needed.  Results are identical either way. */
+int  tanw_set_long_band_rows(tanw_ctx *ctx, int rows);
 /* Pairs with m <= 128 and n <= 4096 are aligned four per warp by the line kernel (8 lanes per
  * pair; BASELINE config 3).  enabled = 0 sends them through the page kernel instead (same
  * results; used by the tests to compare the two paths).  Default: enabled. */

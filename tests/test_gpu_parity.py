@@ -300,6 +300,56 @@ def test_long_path_random_parameters(long_ctx, oracle):
         _check_ctx_vs_oracle(long_ctx, oracle, pairs, params)
 
 
+@pytest.mark.parametrize('rows', [1, 7, 32, 100, 257])
+def test_long_path_row_bands(long_ctx, oracle, rows):
+    """Row-banded chained-pass path (checkpoint at every band edge, bottom-up recompute with the
+    traceback carried across bands): identical op strings and corner scores for every band
+    height, including bands of one row and a last band shorter than the others."""
+    long_ctx.set_long_band_rows(rows)
+    sizes = [(1, 1), (2, 700), (700, 1), (33, 511), (100, 1025), (300, 1100), (801, 520), (257, 2049)]
+    if rows < 32:
+        sizes = sizes[:6]
+    pairs = [synth.make_pair(900 + k, n, m, 2, 30) for k, (n, m) in enumerate(sizes)]
+    _check_ctx_vs_oracle(long_ctx, oracle, pairs)
+    rng = random.Random(rows)
+    pairs = [(''.join(rng.choice('ab') for _ in range(rng.randint(1, 500))),
+              ''.join(rng.choice('ab') for _ in range(rng.randint(1, 1500)))) for _ in range(4)]
+    for params in [(5, -4, -2, -7, 0, -5, -1), (1, -1, -1, -1, -1, -1, -3), (7, 2, -4, 3, -1, 1, 0)]:
+        _check_ctx_vs_oracle(long_ctx, oracle, pairs, params)
+
+
+def test_long_path_row_bands_tabulated_scorer(long_ctx, oracle):
+    import scorers
+    long_ctx.set_long_band_rows(50)
+    rng = random.Random(77)
+    pairs = [(''.join(rng.choice('abcdef') for _ in range(420)), ''.join(rng.choice('abcdef') for _ in range(1300)))]
+    buf, t_off, n, o_off, m = _pack(pairs)
+    table = np.array([[scorers.SCORERS['vowel_aware'](chr(a), chr(b)) if a < 128 and b < 128 else -3
+                       for b in range(128)] for a in range(128)], dtype=np.int32)
+    sc = long_ctx.make_scoring(0, 0, -3, -4, -1, -2, -1, subst=table)
+    ops, ops_off, ops_len, scores = long_ctx.align_batch(buf, t_off, n, o_off, m, sc)
+    long_ctx.set_long_band_rows(0)
+    ops1, _, ops_len1, scores1 = long_ctx.align_batch(buf, t_off, n, o_off, m, sc)
+    assert ops_len.tolist() == ops_len1.tolist() and np.array_equal(ops[:ops_len[0]], ops1[:ops_len1[0]])
+    assert scores.tolist() == scores1.tolist()
+
+
+def test_pair_larger_than_the_arena_is_banded(oracle):
+    """A pair whose pointer block (1 B/cell) exceeds the arena limit is aligned in row bands
+    instead of being refused -- on the chained-pass path and for an oversized page of an ordinary
+    batch alike."""
+    from text_alignment_b200 import _native
+    ctx = _native.Context(0)
+    try:
+        ctx.set_arena_limit(8 << 20)
+        pairs = [synth.make_pair(5100, 9000, 8000, 5, 200)]            # 72 MB of pointers, 2^26 cells
+        _check_ctx_vs_oracle(ctx, oracle, pairs)
+        pairs = [synth.c2_pair(k) for k in range(6)] + [synth.make_pair(5101, 5000, 4000, 5, 200)]
+        _check_ctx_vs_oracle(ctx, oracle, pairs)                       # 20 MB page among 2.7 MB pages
+    finally:
+        ctx.close()
+
+
 def test_long_and_batched_pairs_mixed(tsc, oracle):
     """One batch holding ordinary pages and a pair above the default threshold (2^26 cells)."""
     pairs = [synth.c2_pair(7), synth.make_pair(5002, 9000, 8000, 5, 200), synth.c3_pair(3), synth.c2_pair(8)]
@@ -477,7 +527,9 @@ def test_small_arena_limit_reduces_occupancy_not_correctness(oracle):
         pairs = [synth.c2_pair(300 + k) for k in range(12)] + [synth.c3_pair(k) for k in range(40)]
         ctx.set_arena_limit(24 << 20)                     # room for ~2 CTAs of page slots
         _check_ctx_vs_oracle(ctx, oracle, pairs)
-        ctx.set_arena_limit(1 << 20)                      # smaller than one page slot
+        ctx.set_arena_limit(1 << 20)                      # smaller than one page: row bands
+        _check_ctx_vs_oracle(ctx, oracle, pairs[:14])
+        ctx.set_arena_limit(16 << 10)                     # not even 32 rows of one page
         with pytest.raises(MemoryError):
             ctx.align_batch(*_pack(pairs[:2]), ctx.make_scoring(*DEFAULT))
         ctx.set_arena_limit(0)                            # back to the default

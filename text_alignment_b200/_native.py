@@ -49,6 +49,7 @@ SIGNATURES = {
     'tanw_destroy': (ctypes.c_int, [_VOIDP]),
     'tanw_set_arena_limit': (ctypes.c_int, [_VOIDP, ctypes.c_int64]),
     'tanw_set_long_threshold': (ctypes.c_int, [_VOIDP, ctypes.c_int64]),
+    'tanw_set_long_band_rows': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_set_line_kernel': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_align_batch': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                         ctypes.POINTER(Scoring), _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
@@ -152,6 +153,11 @@ class Context(object):
     def set_long_threshold(self, cells):
         """Pairs with n*m >= cells use the chained-pass (whole-GPU) path; default 2**26."""
         self._check(self._lib.tanw_set_long_threshold(self._h, int(cells)))
+
+    def set_long_band_rows(self, rows):
+        """Cut chained-pass pairs into bands of `rows` rows (checkpoint + recompute); 0 = only
+        when the pointer block would not fit the arena."""
+        self._check(self._lib.tanw_set_long_band_rows(self._h, int(rows)))
 
     def set_line_kernel(self, enabled):
         """Route short pairs (m <= 128) through the four-pairs-per-warp kernel (default on)."""

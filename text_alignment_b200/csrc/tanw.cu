@@ -90,6 +90,9 @@ struct tanw_ctx {
     int long_capacity = 0;                // resident warps for a cooperative launch
     int long_epoch = 0;                   // stamps the chain records of a launch
     DevBuf d_chain;
+    DevBuf d_ck;                          // row-band checkpoints: 4 ints of traceback state, then 3*m ints per band edge
+    std::vector<int2> h_long_geo;         // per long pair: (stripe strip width, rows per band)
+    int long_band_rows = 0;               // 0 = one band unless the pointer block exceeds the arena limit
     int64_t long_cells = int64_t(1) << 26;   // pairs with n*m >= this use the chained-pass path
     pinned_vector<PairDesc> h_pairs;
     pinned_vector<int> h_order, h_order_sorted;
@@ -220,11 +223,31 @@ int long_stripe_c(const tanw_ctx *ctx, int m)
     return kMaxC;
 }
 
-// One whole-manuscript pair on the chained-pass path: init, one cooperative launch per wave
-// of resident stripes, traceback.
-int run_long_pair(tanw_ctx *ctx, int p, int *launches)
+// Rows per band of a chained-pass pair: the whole pair when its pointer block fits `limit`
+// bytes (and no band height is forced), otherwise the tallest band that does.  0 = not even
+// kMinBandRows rows fit.
+constexpr int kMinBandRows = 32;
+int long_band_rows(const tanw_ctx *ctx, int n, int m, int cf, int64_t limit)
+{
+    const int64_t row_bytes = (int64_t)((m + 32 * cf - 1) / (32 * cf)) * 32 * cf;   // ptr_bytes = row_bytes*(rows+32)
+    int64_t rows = limit / std::max<int64_t>(row_bytes, 1) - 32;
+    if (ctx->long_band_rows > 0) rows = std::min<int64_t>(rows, ctx->long_band_rows);
+    if (rows >= n) return std::max(n, 1);
+    return rows >= kMinBandRows || (ctx->long_band_rows > 0 && rows >= ctx->long_band_rows) ? (int)rows : 0;
+}
+
+// One whole-manuscript pair on the chained-pass path: one cooperative launch per wave of
+// resident stripes, then the traceback.  When the pair is cut into row bands (its pointer block
+// would not fit the arena) the fill runs top to bottom once without storing pointers, leaving
+// the per-column state (X, D, W) at every band edge; then, bottom to top, each band is filled
+// again from its checkpoint with pointers stored and the traceback continues through it.
+int run_long_pair(tanw_ctx *ctx, int p, int2 geo, int *launches)
 {
     const PairDesc &pd = ctx->h_pairs[(size_t)p];
+    const int R = geo.y;
+    const int B = (pd.n + R - 1) / R;
+    int *state = (int *)ctx->d_ck.p;
+    int *ck = state + 4;
     LongArgs la;
     la.T = (const uint8_t *)ctx->d_sym.p + pd.t_off;
     la.O = (const uint8_t *)ctx->d_sym.p + pd.o_off;
@@ -232,29 +255,42 @@ int run_long_pair(tanw_ctx *ctx, int p, int *launches)
     la.m = pd.m;
     la.ptr = (uint8_t *)ctx->d_arena.p;
     la.chain = (int4 *)ctx->d_chain.p;
-    la.chain_stride = (long long)pd.n + 4;
-    la.epoch = ++ctx->long_epoch;
-    if (la.epoch == 0) la.epoch = ++ctx->long_epoch;
-    la.pass0 = 0;
-    la.cfull = long_stripe_c(ctx, pd.m);
+    la.chain_stride = (long long)std::min(R, pd.n) + 4;
+    la.cfull = geo.x;
     la.scores = (int *)ctx->d_scores.p + 3 * (size_t)p;
     const int npass = (pd.m + 32 * la.cfull - 1) / (32 * la.cfull);
-    for (int w0 = 0; w0 < npass; w0 += ctx->long_capacity) {
-        la.pass0 = w0;
-        const int grid = std::min(ctx->long_capacity, npass - w0);
-        void *args[] = { (void *)&la, (void *)&ctx->kp };
-        const int var = kernel_variant(ctx);
-        const void *fn = var < 0 ? (const void *)align_long_kernel<true, 0>
-                       : var == 2 ? (const void *)align_long_kernel<false, 2>
-                       : var == 1 ? (const void *)align_long_kernel<false, 1>
-                                  : (const void *)align_long_kernel<false, 0>;
-        TANW_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(32), args, 0, ctx->stream));
+    const int var = kernel_variant(ctx);
+    const void *fn = var < 0 ? (const void *)align_long_kernel<true, 0>
+                   : var == 2 ? (const void *)align_long_kernel<false, 2>
+                   : var == 1 ? (const void *)align_long_kernel<false, 1>
+                              : (const void *)align_long_kernel<false, 0>;
+    auto fill_band = [&](int b, bool store) -> int {
+        la.r0 = b * R;
+        la.nb = std::min(R, pd.n - la.r0);
+        la.ck_in = b > 0 ? ck + (size_t)(b - 1) * 3 * (size_t)pd.m : nullptr;
+        la.ck_out = (!store && b < B - 1) ? ck + (size_t)b * 3 * (size_t)pd.m : nullptr;
+        la.store = store ? 1 : 0;
+        la.epoch = ++ctx->long_epoch;
+        if (la.epoch == 0) la.epoch = ++ctx->long_epoch;
+        for (int w0 = 0; w0 < npass; w0 += ctx->long_capacity) {
+            la.pass0 = w0;
+            const int grid = std::min(ctx->long_capacity, npass - w0);
+            void *args[] = { (void *)&la, (void *)&ctx->kp };
+            TANW_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(32), args, 0, ctx->stream));
+            ++*launches;
+        }
+        return TANW_OK;
+    };
+    for (int b = 0; b < B - 1; ++b)
+        if (int rc = fill_band(b, false)) return rc;
+    for (int b = B - 1; b >= 0; --b) {
+        if (int rc = fill_band(b, true)) return rc;
+        trace_long_kernel<<<1, 32, 0, ctx->stream>>>(la.ptr, pd.n, pd.m, la.cfull, la.r0, la.nb, b == B - 1, b == 0,
+                                                     state, (uint8_t *)ctx->d_ops.p + pd.ops_off,
+                                                     (int *)ctx->d_len.p + p);
+        TANW_CUDA(ctx, cudaGetLastError());
         ++*launches;
     }
-    trace_long_kernel<<<1, 32, 0, ctx->stream>>>(la.ptr, pd.n, pd.m, la.cfull, (uint8_t *)ctx->d_ops.p + pd.ops_off,
-                                                 (int *)ctx->d_len.p + p);
-    TANW_CUDA(ctx, cudaGetLastError());
-    ++*launches;
     return TANW_OK;
 }
 
@@ -364,7 +400,7 @@ int tanw_destroy(tanw_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_pairs, &ctx->d_order, &ctx->d_counter, &ctx->d_arena,
-                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst, &ctx->d_prog, &ctx->d_quads, &ctx->d_chain };
+                       &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores, &ctx->d_subst, &ctx->d_prog, &ctx->d_quads, &ctx->d_chain, &ctx->d_ck };
     for (auto b : bufs) b->release();
     cudaEvent_t evs[] = { ctx->ev_h2d0, ctx->ev_h2d1, ctx->ev_k0, ctx->ev_k1, ctx->ev_d2h0, ctx->ev_d2h1 };
     for (auto ev : evs)
@@ -387,6 +423,15 @@ int tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells)
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     if (cells < 1) return fail(ctx, TANW_E_INVALID, "long-pair threshold must be >= 1 cell");
     ctx->long_cells = cells;
+    return TANW_OK;
+}
+
+int tanw_set_long_band_rows(tanw_ctx *ctx, int rows)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    if (rows < 0) return fail(ctx, TANW_E_INVALID, "band height must be >= 0 rows");
+    ctx->long_band_rows = rows;
+    ctx->prepared = false;
     return TANW_OK;
 }
 
@@ -461,8 +506,11 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
     ctx->h_pairs.resize((size_t)n_pairs);
     ctx->h_ops_off.resize((size_t)n_pairs);
     ctx->h_long.clear();
+    ctx->h_long_geo.clear();
     ctx->h_line.clear();
-    int64_t max_line_slot = 0;
+    int64_t limit = ctx->arena_limit;
+    if (limit == 0) limit = ctx->total_mem / 10 * 4;     // no cudaMemGetInfo on the per-batch path
+    int64_t max_line_slot = 0, max_ck = 0;
     int64_t ops_total = 0, cells = 0, ptr_total = 0, max_nm = 0, max_slot = 0, max_long = 0, max_long_bnd = 0;
     int max_n = 0, max_long_pass = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
@@ -481,14 +529,26 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         // a batch of one or two pages (the drop-in single call) would occupy one or two warps:
         // spread each page over its stripes instead (latency 1.4 ms -> ~0.5 ms per page)
         const bool tiny_batch = n_pairs <= 2 && mp > kLineMaxM && np * mp >= (int64_t(1) << 16);
-        if ((np * mp >= ctx->long_cells || tiny_batch) && ctx->long_capacity > 0) {
+        // a page whose pointer block does not fit one warp's share of the arena goes to the
+        // chained-pass path too, which can cut it into row bands
+        const bool oversize = np > 0 && mp > 0 && (ptr_bytes((int)np, (int)mp) + 255) / 256 * 256 * kWarpsPerBlock > limit &&
+                              !(ctx->use_lines && mp <= kLineMaxM && np <= kLineMaxN);
+        if ((np * mp >= ctx->long_cells || tiny_batch || oversize) && ctx->long_capacity > 0) {
             // whole-manuscript pair: one warp per column stripe, all stripes resident at once
-            ctx->h_long.push_back((int)p);
             const int cf = long_stripe_c(ctx, (int)mp);
             const int64_t npass = (mp + 32 * cf - 1) / (32 * cf);
-            max_long = std::max<int64_t>(max_long, ptr_bytes((int)np, (int)mp, cf));
-            max_long_bnd = std::max(max_long_bnd, (npass + 1) * (np + 4));
+            const int rows = long_band_rows(ctx, (int)np, (int)mp, cf, limit);
+            if (rows <= 0)
+                return fail(ctx, TANW_E_NOMEM, "pair %lld: not even %d rows of traceback pointers (%lld bytes each) "
+                            "fit the arena limit of %lld bytes", (long long)p, kMinBandRows,
+                            (long long)(npass * 32 * cf), (long long)limit);
+            ctx->h_long.push_back((int)p);
+            ctx->h_long_geo.push_back(make_int2(cf, rows));
+            const int64_t bands = (np + rows - 1) / rows;
+            max_long = std::max<int64_t>(max_long, ptr_bytes((int)std::min<int64_t>(rows, np), (int)mp, cf));
+            max_long_bnd = std::max(max_long_bnd, (npass + 1) * (std::min<int64_t>(rows, np) + 4));
             max_long_pass = std::max<int>(max_long_pass, (int)npass);
+            max_ck = std::max(max_ck, (bands - 1) * 3 * mp);
         } else if (ctx->use_lines && mp <= kLineMaxM && np <= kLineMaxN) {
             // short pair: 8 lanes per pair, four pairs per warp
             ctx->h_line.push_back((int)p);
@@ -591,17 +651,12 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
     const int64_t need_blocks = (n_batch + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (need_blocks < grid) grid = (int)std::max<int64_t>(need_blocks, 1);
     const int64_t slot_bytes = (max_slot + 255) / 256 * 256;
-    int64_t limit = ctx->arena_limit;
-    if (limit == 0) limit = ctx->total_mem / 10 * 4;     // no cudaMemGetInfo on the per-batch path
-    if (max_long > (int64_t)(limit / 4 * 9))
-        return fail(ctx, TANW_E_NOMEM, "a pair needs %lld bytes of traceback pointers; arena limit is %lld",
-                    (long long)max_long, (long long)limit);
     if (slot_bytes > 0) {
         int64_t max_blocks = limit / (slot_bytes * kWarpsPerBlock);
         if (max_blocks < 1)
             return fail(ctx, TANW_E_NOMEM,
                         "a pair needs %lld bytes of traceback pointers per warp; arena limit is %lld "
-                        "(use the striped long-pair path)", (long long)slot_bytes, (long long)limit);
+                        "and this device cannot run the chained-pass path", (long long)slot_bytes, (long long)limit);
         if (max_blocks < grid) grid = (int)max_blocks;
     }
     ctx->grid = grid;
@@ -622,6 +677,7 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         ctx->d_quads.reserve(sizeof(int4) * (size_t)std::max<int64_t>(n_quads, 1)) != cudaSuccess ||
         ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(slots * bnd_rows, 1)) != cudaSuccess ||
         reserve_zeroed(ctx, ctx->d_chain, sizeof(int4) * (size_t)max_long_bnd) != cudaSuccess ||
+        ctx->d_ck.reserve(sizeof(int) * (size_t)(4 + max_ck)) != cudaSuccess ||
         ctx->d_ops.reserve((size_t)ops_total + 64) != cudaSuccess ||
         ctx->d_len.reserve(sizeof(int) * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess ||
         ctx->d_scores.reserve(sizeof(int) * 3 * (size_t)std::max<int64_t>(n_pairs, 1)) != cudaSuccess) {
@@ -744,8 +800,8 @@ int tanw_batch_run(tanw_ctx *ctx)
         TANW_CUDA(ctx, cudaGetLastError());
         ++launches;
     }
-    for (int p : ctx->h_long) {
-        int rc = run_long_pair(ctx, p, &launches);
+    for (size_t i = 0; i < ctx->h_long.size(); ++i) {
+        int rc = run_long_pair(ctx, ctx->h_long[i], ctx->h_long_geo[i], &launches);
         if (rc) return rc;
     }
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));

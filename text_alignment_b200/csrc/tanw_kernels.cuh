@@ -227,6 +227,7 @@ struct PassState {
     const int2 *bp;        // &bnd[t+2]: next boundary row to prefetch
     int2 *bw;              // &bnd[i+1]: where lane 31 leaves its right edge next
     uint8_t *pst;          // pointer bytes of this lane for the next step
+    int c0;                // 0-based first column of the strip
     int2 blk_cur;          // chained passes: current 8-row block of the left boundary, one row per lane 0..7
     int4 blk_raw;          // chained passes: the next block as loaded (stamps not yet checked)
 };
@@ -242,7 +243,21 @@ struct Chain {
     int4 *out;             // records this stripe produces
     int epoch;             // nonzero, unique per launch
     bool first;            // stripe 0: the left boundary is column 0 of the matrices
+    // Row bands (pairs whose pointer matrix does not fit the arena): a launch covers rows
+    // r0+1 .. r0+n of the matrix, starting from the per-column state saved at row r0.
+    int r0;                // rows above the band (0: start from the matrix's row 0)
+    const int *ck_in;      // state at row r0: X (real, tagged) [m], D [m], W [m]; null when r0 == 0
+    int *ck_out;           // where to leave the state of the band's last row, or null
+    int m;                 // columns = stride of the checkpoint arrays
+    bool store;            // write pointer bytes (false in the forward checkpointing sweep)
 };
+__device__ __forceinline__ Chain no_chain()
+{
+    Chain c;
+    c.in = nullptr; c.out = nullptr; c.epoch = 0; c.first = false;
+    c.r0 = 0; c.ck_in = nullptr; c.ck_out = nullptr; c.m = 0; c.store = true;
+    return c;
+}
 constexpr int kChainBlock = 8;         // boundary rows fetched per coalesced load (lanes 0..7)
 
 __device__ __forceinline__ int4 ld_volatile_v4(const int4 *p)
@@ -294,7 +309,7 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
             // (one coalesced load per block, fetched a block ahead) and reaches lane 0 by shuffle.
             const int r = t + 1;                          // boundary row needed by the next step
             if (ch.first) {
-                ps.bnext = make_int2((kp.bg * r) | kTagM, kp.bg * r);       // column 0 (:54-56)
+                ps.bnext = make_int2((kp.bg * (ch.r0 + r)) | kTagM, kp.bg * (ch.r0 + r));   // column 0 (:54-56)
             } else {
                 const int j = (r - 1) & (kChainBlock - 1);
                 if (j == 0) {                     // rows r .. r+7 were requested 8 steps ago
@@ -316,10 +331,22 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
         const int kfin = (GUARDED && i == n && lane == fin_lane) ? fin_k : -1;
         strip_row<C, GUARDED, SUBST, VAR>(s, kp, tch, ps.xe, ps.cx, q_in, y_in, dul_in,
                                           ps.q_out, ps.y_out, pw, kfin, cap);
-        store_ptr_words<C>(ps.pst, pw);
+        if (!CHAINED || ch.store) store_ptr_words<C>(ps.pst, pw);
         if (has_next && lane == 31) {
             if (CHAINED) st_volatile_v4(ch.out + i, make_int4(ps.q_out, ch.epoch, ps.y_out, ch.epoch));
             else         __stcg(ps.bw, make_int2(ps.q_out, ps.y_out));
+        }
+        if (CHAINED && GUARDED && ch.ck_out != nullptr && i == n) {
+            // last row of a band: leave the per-column state for the launch that continues below
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const int col = ps.c0 + k;
+                if (col < ch.m) {
+                    ch.ck_out[col] = s.Xh[k] + ps.xe;             // X^ back to the real (tagged) X
+                    ch.ck_out[ch.m + col] = s.D[k];
+                    if (VAR == 0) ch.ck_out[2 * ch.m + col] = s.W[k];
+                }
+            }
         }
     }
     ps.q_prev = q_in;
@@ -359,17 +386,27 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
         s.W[k] = base | kTagM;
         s.Xh[k] = base | kTagX;
         s.D[k] = base | kTagM;
+        if (CHAINED && ch.ck_in != nullptr && c < m) {        // a band that starts below row 0
+            s.Xh[k] = ch.ck_in[c];
+            s.D[k] = ch.ck_in[ch.m + c];
+            if (VAR == 0) s.W[k] = ch.ck_in[2 * ch.m + c];
+        }
     }
     PassState ps;
+    ps.c0 = c0;
     ps.q_out = (kp.bg * (c0 + C)) | kTagM;        // right edge of row 0
     ps.y_out = kNeg;
     ps.q_prev = (kp.bg * c0) | kTagM;             // left neighbour column, row 0
     ps.y_prev = kNeg;                             // (Y[0][j] = -inf, also at j = 0)
+    if (CHAINED && ch.ck_in != nullptr) {         // the same two edges at row r0 (D >= Q, Y not needed)
+        ps.q_out = (c0 + C - 1 < m) ? ch.ck_in[ch.m + c0 + C - 1] : 0;
+        ps.q_prev = (c0 == 0) ? ((kp.bg * ch.r0) | kTagM) : ((c0 - 1 < m) ? ch.ck_in[ch.m + c0 - 1] : 0);
+    }
     ps.blk_cur = make_int2(0, 0);
     ps.blk_raw = make_int4(0, 0, 0, 0);
     if (CHAINED) {
         if (ch.first) {
-            ps.bnext = make_int2(kp.bg | kTagM, kp.bg);                     // row 1 of column 0
+            ps.bnext = make_int2((kp.bg * (ch.r0 + 1)) | kTagM, kp.bg * (ch.r0 + 1));   // first row of column 0
         } else {
             ps.blk_cur = chain_take(ch, chain_issue(ch, 1, n, lane), 1, n, lane);       // rows 1..8
             if (1 + kChainBlock <= n) ps.blk_raw = chain_issue(ch, 1 + kChainBlock, n, lane);
@@ -476,66 +513,80 @@ constexpr int kTileStride = kTileWords + 1;        // words per tile row in shar
 // x-32-r, 32 independent word loads), then lane 0 walks inside the tile.  Ops are written back
 // to front at the END of the pair's op buffer (capacity n+m); returns the number of columns
 // (valid in every lane).
+// The tile loop: walks from local cell (x, y) in state st (-1: take mat_ptr first) until the top
+// row or the left column of this pointer block is reached; x, y, st, k are updated in every lane.
+__device__ __forceinline__ void traceback_core(const uint8_t *ptr, int n, int m, int cfull,
+                                               uint8_t *ops_end, unsigned *tile, int lane,
+                                               int &x, int &y, int &st, int &k)
+{
+    const PtrMap map(n, m, cfull);
+    while (x > 0 && y > 0) {
+        // ---- tile load: word columns wq_hi-15 .. wq_hi, rows x-lane and x-32-lane ----------
+        const int wq_hi = (y - 1) >> 2;
+        const int row0 = x - lane, row1 = x - 32 - lane;
+        unsigned w0[kTileWords], w1[kTileWords];
+        PtrCursor cur;
+        cur.seek(map, wq_hi);
+#pragma unroll
+        for (int q = kTileWords - 1; q >= 0; --q) {
+            const int wq = wq_hi - (kTileWords - 1 - q);
+            w0[q] = 0u; w1[q] = 0u;
+            if (wq >= 0) {
+                if (row0 >= 1) w0[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row0)));
+                if (row1 >= 1) w1[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row1)));
+                if (wq > 0) cur.left(map);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kTileWords; ++q) {
+            tile[lane * kTileStride + q] = w0[q];
+            tile[(lane + 32) * kTileStride + q] = w1[q];
+        }
+        __syncwarp();
+        // ---- walk inside the tile ---------------------------------------------------------
+        // state 0: diagonal, next = mat_ptr; 1: x-gap, next = x_mat_ptr; 2: y-gap, next =
+        // y_mat_ptr (:115-145).  One lane, a chain of dependent shared-memory loads: the loop
+        // keeps only  load -> shift -> mask -> subtract  on that chain (byte-addressed tile,
+        // running offset, exit counters that do not depend on the loaded byte).
+        if (lane == 0) {
+            const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
+            const int col_lo = (wq_hi - (kTileWords - 1)) * 4;      // 0-based column of tile byte 0
+            int off = (y - 1) - col_lo;                             // row 0 of the tile, 60..63
+            if (st < 0) st = 2 - (int)(tb[off] & 3u);                                 // :102
+            const int xr0 = min(x, kTileRows), yr0 = min(y, off + 1);
+            int xr = xr0, yr = yr0;                                 // row / column moves left here
+            while (xr > 0 && yr > 0) {
+                const unsigned b = tb[off];
+                const int dx = (st != 2), dy = (st != 1);
+                ++k;
+                *(ops_end - k) = (uint8_t)st;
+                off += dx * (kTileStride * 4) - dy;
+                xr -= dx;
+                yr -= dy;
+                st = 2 - (int)((b >> (2 * st)) & 3u);
+            }
+            x -= xr0 - xr;
+            y -= yr0 - yr;
+        }
+        x = __shfl_sync(kFull, x, 0);
+        y = __shfl_sync(kFull, y, 0);
+        st = __shfl_sync(kFull, st, 0);
+        k = __shfl_sync(kFull, k, 0);
+    }
+}
+
+// Traceback of one pair (textSeqCompare.py:96-164) by one warp.  The pointer chase is a chain
+// of dependent loads, so the warp first pulls the 64-row x 64-column tile of pointer bytes
+// whose bottom-right corner is the current cell into shared memory (lane r: rows x-r and
+// x-32-r, 32 independent word loads), then lane 0 walks inside the tile.  Ops are written back
+// to front at the END of the pair's op buffer (capacity n+m); returns the number of columns
+// (valid in every lane).
 __device__ __forceinline__ int traceback_warp(const uint8_t *ptr, int n, int m, int cfull,
                                               uint8_t *ops_end, unsigned *tile, int lane)
 {
-    int x = n, y = m, k = 0;
-    if (n > 0 && m > 0) {
-        const PtrMap map(n, m, cfull);
-        int st = -1;                                       // -1: take mat_ptr[n][m] first (:102)
-        while (x > 0 && y > 0) {
-            // ---- tile load: word columns wq_hi-15 .. wq_hi, rows x-lane and x-32-lane ------
-            const int wq_hi = (y - 1) >> 2;
-            const int row0 = x - lane, row1 = x - 32 - lane;
-            unsigned w0[kTileWords], w1[kTileWords];
-            PtrCursor cur;
-            cur.seek(map, wq_hi);
-#pragma unroll
-            for (int q = kTileWords - 1; q >= 0; --q) {
-                const int wq = wq_hi - (kTileWords - 1 - q);
-                w0[q] = 0u; w1[q] = 0u;
-                if (wq >= 0) {
-                    if (row0 >= 1) w0[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row0)));
-                    if (row1 >= 1) w1[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row1)));
-                    if (wq > 0) cur.left(map);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < kTileWords; ++q) {
-                tile[lane * kTileStride + q] = w0[q];
-                tile[(lane + 32) * kTileStride + q] = w1[q];
-            }
-            __syncwarp();
-            // ---- walk inside the tile -----------------------------------------------------
-            // state 0: diagonal, next = mat_ptr; 1: x-gap, next = x_mat_ptr; 2: y-gap, next =
-            // y_mat_ptr (:115-145).  One lane, a chain of dependent shared-memory loads: the loop
-            // keeps only  load -> shift -> mask -> subtract  on that chain (byte-addressed tile,
-            // running offset, exit counters that do not depend on the loaded byte).
-            if (lane == 0) {
-                const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
-                const int col_lo = (wq_hi - (kTileWords - 1)) * 4;      // 0-based column of tile byte 0
-                int off = (y - 1) - col_lo;                             // row 0 of the tile, 60..63
-                if (st < 0) st = 2 - (int)(tb[off] & 3u);                             // :102
-                const int xr0 = min(x, kTileRows), yr0 = min(y, off + 1);
-                int xr = xr0, yr = yr0;                                 // row / column moves left here
-                while (xr > 0 && yr > 0) {
-                    const unsigned b = tb[off];
-                    const int dx = (st != 2), dy = (st != 1);
-                    ++k;
-                    *(ops_end - k) = (uint8_t)st;
-                    off += dx * (kTileStride * 4) - dy;
-                    xr -= dx;
-                    yr -= dy;
-                    st = 2 - (int)((b >> (2 * st)) & 3u);
-                }
-                x -= xr0 - xr;
-                y -= yr0 - yr;
-            }
-            x = __shfl_sync(kFull, x, 0);
-            y = __shfl_sync(kFull, y, 0);
-        }
-    }
+    int x = n, y = m, k = 0, st = -1;
+    if (n > 0 && m > 0) traceback_core(ptr, n, m, cfull, ops_end, tile, lane, x, y, st, k);
     if (lane == 0) {
         while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // OCR remainder first       (:154-158)
         while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // then transcript remainder (:160-164)
@@ -596,7 +647,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
                 const int fin_k = last ? cc % C : -1;
                 dispatch_pass<SUBST, VAR, false>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
                                                  ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap,
-                                                 Chain{nullptr, nullptr, 0, false});
+                                                 no_chain());
                 __syncwarp();
             }
             // the lane that owns column m holds the corner scores
@@ -887,14 +938,18 @@ align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
 // (1 byte/cell; 8 GB for config 5), and the ordinary tile-prefetch traceback runs afterwards.
 struct LongArgs {
     const uint8_t *T, *O;
-    int n, m;
-    uint8_t *ptr;          // ptr_bytes(n, m, cfull)
+    int n, m;              // the whole pair
+    int r0, nb;            // this launch: rows r0+1 .. r0+nb (one band; r0 = 0, nb = n without banding)
+    uint8_t *ptr;          // ptr_bytes(nb, m, cfull) when store != 0
     int4 *chain;           // npass arrays of chain_stride records; array w = right edge of stripe w
     long long chain_stride;
     int epoch;             // nonzero, unique per launch within the context
     int pass0;             // first stripe handled by this launch (waves when stripes > resident warps)
     int cfull;             // stripe strip width: a full stripe has 32*cfull columns
-    int *scores;           // 3 ints
+    const int *ck_in;      // per-column state at row r0 (3*m ints) or null when r0 == 0
+    int *ck_out;           // where to leave the state at row r0+nb (3*m ints) or null
+    int store;             // write pointer bytes
+    int *scores;           // 3 ints, written by the launch that contains row n (or null)
 };
 
 template <bool SUBST, int VAR>
@@ -902,7 +957,7 @@ __global__ void __launch_bounds__(32, 8)
 align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
 {
     const int w = a.pass0 + blockIdx.x;
-    const int n = a.n, m = a.m;
+    const int n = a.nb, m = a.m;
     const int passw = 32 * a.cfull;
     const int nfull = m / passw, r = m % passw;
     const int npass = nfull + (r ? 1 : 0);
@@ -920,22 +975,45 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
     ch.out = a.chain + (size_t)w * (size_t)a.chain_stride;
     ch.epoch = a.epoch;
     ch.first = (w == 0);
-    dispatch_pass<SUBST, VAR, true>(C, kp, a.T, a.O, n, m, j0, !last, nullptr, nullptr,
+    ch.r0 = a.r0;
+    ch.ck_in = a.ck_in;
+    ch.ck_out = a.ck_out;
+    ch.m = m;
+    ch.store = a.store != 0;
+    dispatch_pass<SUBST, VAR, true>(C, kp, a.T + a.r0, a.O, n, m, j0, !last, nullptr, nullptr,
                                     a.ptr + (size_t)w * (size_t)pass_bytes, fin_lane, fin_k, cap, ch);
-    if (last && (int)(threadIdx.x & 31) == fin_lane && a.scores) {
+    if (last && (int)(threadIdx.x & 31) == fin_lane && a.scores && a.r0 + a.nb == a.n) {
         a.scores[0] = score_out(cap[0]);
         a.scores[1] = score_out(cap[1]);
         a.scores[2] = score_out(cap[2]);
     }
 }
 
+// Traceback of one band of a chained-stripe pair.  state = {x, y, st, k} persists between bands
+// (x, y in matrix coordinates); `init` starts at (n, m), `final` flushes the remainders
+// (textSeqCompare.py:154-164) and moves the op string to the start of its buffer.
 __global__ void __launch_bounds__(32)
-trace_long_kernel(const uint8_t *ptr, int n, int m, int cfull, uint8_t *ops, int *ops_len)
+trace_long_kernel(const uint8_t *ptr, int n, int m, int cfull, int r0, int nb, int init, int final,
+                  int *state, uint8_t *ops, int *ops_len)
 {
     __shared__ unsigned tile[kTileRows * kTileStride];
     const int lane = threadIdx.x & 31;
-    const int L = traceback_warp(ptr, n, m, cfull, ops + (size_t)n + (size_t)m, tile, lane);
-    if (lane == 0) *ops_len = L;
+    uint8_t *ops_end = ops + (size_t)n + (size_t)m;
+    int x = init ? n : state[0], y = init ? m : state[1], st = init ? -1 : state[2], k = init ? 0 : state[3];
+    __syncwarp();
+    int xl = x - r0;                                       // row inside this band's pointer block
+    if (xl > 0 && y > 0) traceback_core(ptr, nb, m, cfull, ops_end, tile, lane, xl, y, st, k);
+    x = xl + r0;
+    if (!final) {
+        if (lane == 0) { state[0] = x; state[1] = y; state[2] = st; state[3] = k; }
+        return;
+    }
+    if (lane == 0) {
+        while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // :154-158
+        while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // :160-164
+        *ops_len = k;
+    }
+    const int L = __shfl_sync(kFull, k, 0);
     const int shift = n + m - L;
     if (shift > 0) {
         for (int base = 0; base < L; base += 32) {
