@@ -901,7 +901,7 @@ int tanw_last_timing(tanw_ctx *ctx, tanw_timing *out)
 int tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s)
 {
     if (!ctx || !lane_ops_per_s) return fail(ctx, TANW_E_INVALID, "NULL argument");
-    if (which < 0 || which > 2) return fail(ctx, TANW_E_INVALID, "which must be 0, 1 or 2");
+    if (which < 0 || which > 3) return fail(ctx, TANW_E_INVALID, "which must be 0, 1, 2 or 3");
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->d_counter.reserve(256) != cudaSuccess || ctx->d_scores.reserve(4096 * sizeof(int)) != cudaSuccess)
         return fail(ctx, TANW_E_NOMEM, "device allocation failed");
@@ -915,15 +915,16 @@ int tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s)
     for (int rep = 0; rep < 4; ++rep) {
         TANW_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
         int *sink = (int *)ctx->d_counter.p + 8;
-        if (which == 0)      int32_peak_kernel<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink);
-        else if (which == 1) int32_peak_kernel<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink);
-        else                 int32_peak_kernel<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink);
+        if (which == 0)      int32_peak_kernel<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink, 3, 5);
+        else if (which == 1) int32_peak_kernel<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink, 3, 5);
+        else if (which == 2) int32_peak_kernel<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink, 3, 5);
+        else                 int32_peak_kernel<3><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink, 3, 5);
         TANW_CUDA(ctx, cudaGetLastError());
         TANW_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
         TANW_CUDA(ctx, cudaEventSynchronize(e1));
         float ms = 0.f;
         TANW_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
-        // instructions per chain-iteration: IADD3 x1 (two adds merged), VIMNMX x2, VIADDMNMX x2
+        // instructions per chain-iteration: IADD3 x1 (two adds merged), VIMNMX x2, VIADDMNMX x2, VIADD + LOP3
         const double instr = (double)blocks * threads * (double)iters * 16.0 * (which == 0 ? 1.0 : 2.0);
         if (rep > 0) best = std::max(best, instr / (ms * 1e-3));
     }

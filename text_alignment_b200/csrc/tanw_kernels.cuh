@@ -1032,10 +1032,15 @@ trace_long_kernel(const uint8_t *ptr, int n, int m, int cfull, int r0, int nb, i
 //   WHICH 0: two add.s32 per chain-iteration, which ptxas merges into ONE 3-input IADD3
 //   WHICH 1: max.s32 + min.s32  -> two VIMNMX
 //   WHICH 2: fused add+max, add+min -> two VIADDMNMX
-// The host counts INSTRUCTIONS (1, 2, 2 per chain-iteration); see tools/int32_pipes.cu for
+//   WHICH 3: add of a uniform (kernel-parameter) value + xor -> one VIADD, which either integer
+//            pipe executes, + one LOP3 (alu pipe): both pipes busy, i.e. the warp-instruction
+//            issue rate -- the ceiling of a kernel that mixes the pipes as strip_row does.
+//            (VIMNMX + a three-register IMAD reaches only ~88 lanes/clk/SM: tools/int32_pipes.cu)
+// The host counts INSTRUCTIONS (1, 2, 2, 2 per chain-iteration); see tools/int32_pipes.cu for
 // the full table of pipes.
 template <int WHICH>
-__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, const int *__restrict__ src, int *sink)
+__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, const int *__restrict__ src, int *sink,
+                                                         int c1, int c2)
 {
     int x[16], a[16], b[16];
 #pragma unroll
@@ -1053,9 +1058,12 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(int iters, const int *_
             } else if (WHICH == 1) {
                 asm volatile("max.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(a[j]));
                 asm volatile("min.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(b[j]));
-            } else {
+            } else if (WHICH == 2) {
                 x[j] = __viaddmax_s32(x[j], a[j], b[j]);
                 x[j] = __viaddmin_s32(x[j], b[j], a[j]);
+            } else {
+                asm volatile("add.s32 %0, %0, %1;" : "+r"(x[j]) : "r"(c1));
+                asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[j]) : "r"(c2));
             }
         }
     }

@@ -15,6 +15,7 @@ rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 123)
 ctx = _native.Context(0)
 long_ctx = _native.Context(0); long_ctx.set_long_threshold(1)
+band_ctx = _native.Context(0); band_ctx.set_long_threshold(1)       # chained stripes cut into row bands
 total = 0
 t0 = time.time()
 for rd in range(rounds):
@@ -46,6 +47,9 @@ for rd in range(rounds):
     want = nw_oracle.align_batch_codes(*b, sc, threads=16)
     wscore = np.where(want[3] <= -1e99, -1073741824, want[3])
     use = [ctx] + ([long_ctx] if len(pairs) <= 60 else [])
+    if len(pairs) <= 25 and shape != 'tall':
+        band_ctx.set_long_band_rows(rng.choice([3, 17, 40, 64, 129, 300]))
+        use.append(band_ctx)
     for c in use:
         got = c.align_batch(*b, c.make_scoring(*params))
         assert np.array_equal(got[2], want[2]), (rd, shape, params)
