@@ -160,7 +160,8 @@ int  tanw_stream_handle(tanw_ctx *ctx, uint64_t *out);
  * INSTRUCTIONS per second issued from every SM, 16 independent chains per thread.
  * `which`: 0 = IADD3 (add.s32), 1 = VIMNMX (max.s32/min.s32), 2 = VIADDMNMX (fused add+max),
  *          3 = VIADD + LOP3 alternating: both integer pipes busy (VIADD runs on either), i.e.
- *              the issue ceiling of a kernel that mixes the pipes. */
+ *              the issue ceiling of a kernel that mixes the pipes.
+ * Uses the context's scratch buffers: a prepared batch must be prepared again afterwards. */
 int  tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s);
 
 #ifdef __cplusplus

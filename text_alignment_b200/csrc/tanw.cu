@@ -903,14 +903,19 @@ int tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s)
     if (!ctx || !lane_ops_per_s) return fail(ctx, TANW_E_INVALID, "NULL argument");
     if (which < 0 || which > 3) return fail(ctx, TANW_E_INVALID, "which must be 0, 1, 2 or 3");
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->prepared = ctx->ran = false;                     // borrows the score / counter buffers of the batch
     if (ctx->d_counter.reserve(256) != cudaSuccess || ctx->d_scores.reserve(4096 * sizeof(int)) != cudaSuccess)
         return fail(ctx, TANW_E_NOMEM, "device allocation failed");
     const int iters = 1 << 13, blocks = ctx->sm_count * 8, threads = 256;
     const int *src = (const int *)ctx->d_scores.p;       // any initialised words will do
     TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_scores.p, 1, 4096 * sizeof(int), ctx->stream));
-    cudaEvent_t e0, e1;
-    TANW_CUDA(ctx, cudaEventCreate(&e0));
-    TANW_CUDA(ctx, cudaEventCreate(&e1));
+    struct EventPair {                                    // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    TANW_CUDA(ctx, cudaEventCreate(&ev.a));
+    TANW_CUDA(ctx, cudaEventCreate(&ev.b));
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         TANW_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
@@ -928,8 +933,6 @@ int tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s)
         const double instr = (double)blocks * threads * (double)iters * 16.0 * (which == 0 ? 1.0 : 2.0);
         if (rep > 0) best = std::max(best, instr / (ms * 1e-3));
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     *lane_ops_per_s = best;
     return TANW_OK;
 }
