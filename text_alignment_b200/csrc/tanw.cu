@@ -272,6 +272,10 @@ int run_long_pair(tanw_ctx *ctx, int p, int2 geo, int *launches)
         la.store = store ? 1 : 0;
         la.epoch = ++ctx->long_epoch;
         if (la.epoch == 0) la.epoch = ++ctx->long_epoch;
+        long_col0_kernel<<<(la.nb + 255) / 256, 256, 0, ctx->stream>>>(
+            la.chain + (size_t)npass * (size_t)la.chain_stride, la.nb, la.r0, ctx->kp.bg, la.epoch);
+        TANW_CUDA(ctx, cudaGetLastError());
+        ++*launches;
         for (int w0 = 0; w0 < npass; w0 += ctx->long_capacity) {
             la.pass0 = w0;
             const int grid = std::min(ctx->long_capacity, npass - w0);

@@ -222,6 +222,7 @@ struct PassState {
     int q_prev, y_prev;    // what the left neighbour sent in the previous step (row i-1)
     int2 bnext;            // left boundary of the pass for the next step's row (used by lane 0)
     int tnext;             // transcript symbol of the row this lane computes next
+    int tnext2;            // ... and of the row after that (chained stripes prefetch two steps ahead)
     int xe, cx;            // ex*i and ox - ex*i of the row this lane computes next
     const uint8_t *tp;     // &T[i] for the next step (row i+1 reads T[i])
     const int2 *bp;        // &bnd[t+2]: next boundary row to prefetch
@@ -242,7 +243,6 @@ struct Chain {
     const int4 *in;        // records of the stripe to the left, indexed by row (unused if first)
     int4 *out;             // records this stripe produces
     int epoch;             // nonzero, unique per launch
-    bool first;            // stripe 0: the left boundary is column 0 of the matrices
     // Row bands (pairs whose pointer matrix does not fit the arena): a launch covers rows
     // r0+1 .. r0+n of the matrix, starting from the per-column state saved at row r0.
     int r0;                // rows above the band (0: start from the matrix's row 0)
@@ -254,7 +254,7 @@ struct Chain {
 __device__ __forceinline__ Chain no_chain()
 {
     Chain c;
-    c.in = nullptr; c.out = nullptr; c.epoch = 0; c.first = false;
+    c.in = nullptr; c.out = nullptr; c.epoch = 0;
     c.r0 = 0; c.ck_in = nullptr; c.ck_out = nullptr; c.m = 0; c.store = true;
     return c;
 }
@@ -307,25 +307,29 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
             // A chained stripe has an SM sub-partition almost to itself, so a load issued one
             // step ahead does not hide L2 latency.  The boundary arrives in blocks of 8 rows
             // (one coalesced load per block, fetched a block ahead) and reaches lane 0 by shuffle.
+            // Stripe 0 reads column 0 of the matrices the same way (records written by
+            // long_col0_kernel), so that the loop has no per-stripe special case.
             const int r = t + 1;                          // boundary row needed by the next step
-            if (ch.first) {
-                ps.bnext = make_int2((kp.bg * (ch.r0 + r)) | kTagM, kp.bg * (ch.r0 + r));   // column 0 (:54-56)
-            } else {
-                const int j = (r - 1) & (kChainBlock - 1);
-                if (j == 0) {                     // rows r .. r+7 were requested 8 steps ago
-                    ps.blk_cur = chain_take(ch, ps.blk_raw, r, n, lane);
-                    if (r + kChainBlock <= n) ps.blk_raw = chain_issue(ch, r + kChainBlock, n, lane);
-                }
-                ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, j);
-                ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, j);
+            const int j = (r - 1) & (kChainBlock - 1);
+            if (j == 0) {                         // rows r .. r+7 were requested 8 steps ago
+                ps.blk_cur = chain_take(ch, ps.blk_raw, r, n, lane);
+                if (r + kChainBlock <= n) ps.blk_raw = chain_issue(ch, r + kChainBlock, n, lane);
             }
+            ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, j);
+            ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, j);
         } else {
             ps.bnext = __ldcg(ps.bp);             // same address in every lane
         }
     }
     const int dul_in = (VAR >= 1) ? ps.q_prev : max(ps.q_prev, ps.y_prev);   // D of (i-1, left neighbour column)
     const int tch = ps.tnext;
-    if (!GUARDED || (i >= 0 && i < n)) ps.tnext = (int)__ldg(ps.tp);     // row i+1 reads T[i]
+    if (CHAINED) {
+        // a stripe has its scheduler to itself: one step does not cover the load latency
+        ps.tnext = ps.tnext2;
+        if (!GUARDED || (i + 1 >= 0 && i + 1 < n)) ps.tnext2 = (int)__ldg(ps.tp + 1);   // row i+2 reads T[i+1]
+    } else {
+        if (!GUARDED || (i >= 0 && i < n)) ps.tnext = (int)__ldg(ps.tp);     // row i+1 reads T[i]
+    }
     if (!GUARDED || (i >= 1 && i <= n)) {
         unsigned pw[C / 4];
         const int kfin = (GUARDED && i == n && lane == fin_lane) ? fin_k : -1;
@@ -405,20 +409,21 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     ps.blk_cur = make_int2(0, 0);
     ps.blk_raw = make_int4(0, 0, 0, 0);
     if (CHAINED) {
-        if (ch.first) {
-            ps.bnext = make_int2((kp.bg * (ch.r0 + 1)) | kTagM, kp.bg * (ch.r0 + 1));   // first row of column 0
-        } else {
-            ps.blk_cur = chain_take(ch, chain_issue(ch, 1, n, lane), 1, n, lane);       // rows 1..8
-            if (1 + kChainBlock <= n) ps.blk_raw = chain_issue(ch, 1 + kChainBlock, n, lane);
-            ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, 0);
-            ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, 0);
-        }
+        ps.blk_cur = chain_take(ch, chain_issue(ch, 1, n, lane), 1, n, lane);           // rows 1..8
+        if (1 + kChainBlock <= n) ps.blk_raw = chain_issue(ch, 1 + kChainBlock, n, lane);
+        ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, 0);
+        ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, 0);
     } else {
         ps.bnext = __ldcg(bnd + 1);
     }
     ps.bp = bnd + 2;
     ps.bw = bnd_out + (1 - lane);
     ps.tnext = (lane == 0) ? (int)__ldg(T) : 0;
+    ps.tnext2 = 0;
+    if (CHAINED) {
+        if (lane == 0 && n > 1) ps.tnext2 = (int)__ldg(T + 1);
+        if (lane == 1) ps.tnext2 = (int)__ldg(T);
+    }
     ps.tp = T + (1 - lane);
     ps.xe = kp.ex * (1 - lane);                   // row i = t - lane at t = 1
     ps.cx = kp.ox - ps.xe;
@@ -971,10 +976,9 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
     int cap[3] = {0, 0, 0};
     const long long pass_bytes = ((long long)n + 32) * passw;
     Chain ch;
-    ch.in = (w > 0) ? a.chain + (size_t)(w - 1) * (size_t)a.chain_stride : nullptr;
+    ch.in = a.chain + (size_t)(w > 0 ? w - 1 : npass) * (size_t)a.chain_stride;   // array npass: column 0
     ch.out = a.chain + (size_t)w * (size_t)a.chain_stride;
     ch.epoch = a.epoch;
-    ch.first = (w == 0);
     ch.r0 = a.r0;
     ch.ck_in = a.ck_in;
     ch.ck_out = a.ck_out;
@@ -986,6 +990,18 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
         a.scores[0] = score_out(cap[0]);
         a.scores[1] = score_out(cap[1]);
         a.scores[2] = score_out(cap[2]);
+    }
+}
+
+// Column 0 of the matrices for rows r0+1 .. r0+nb as hand-over records (textSeqCompare.py:54-56:
+// M[i][0] = Y[i][0] = gap_extend * i; the Q slot carries the M tag), so that stripe 0 consumes its
+// left boundary exactly like every other stripe.
+__global__ void long_col0_kernel(int4 *rec, int nb, int r0, int bg, int epoch)
+{
+    const int r = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= nb) {
+        const int v = bg * (r0 + r);
+        rec[r] = make_int4(v | kTagM, epoch, v, epoch);
     }
 }
 
