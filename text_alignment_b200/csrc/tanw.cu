@@ -287,8 +287,10 @@ int run_long_pair(tanw_ctx *ctx, int p, int2 geo, int *launches)
     };
     for (int b = 0; b < B - 1; ++b)
         if (int rc = fill_band(b, false)) return rc;
+    static const bool skip_trace = getenv("TANW_DEBUG_SKIP_TRACE") != nullptr;   // timing experiments only
     for (int b = B - 1; b >= 0; --b) {
         if (int rc = fill_band(b, true)) return rc;
+        if (skip_trace) continue;
         trace_long_kernel<<<1, 32, 0, ctx->stream>>>(la.ptr, pd.n, pd.m, la.cfull, la.r0, la.nb, b == B - 1, b == 0,
                                                      state, (uint8_t *)ctx->d_ops.p + pd.ops_off,
                                                      (int *)ctx->d_len.p + p);
