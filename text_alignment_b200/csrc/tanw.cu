@@ -82,6 +82,7 @@ struct tanw_ctx {
 
     DevBuf d_sym, d_pairs, d_order, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_prog, d_quads;
     std::vector<int> h_line;              // pairs routed to the four-per-warp line kernel
+    std::vector<int> h_line_key, h_line_count, h_line_sorted, h_line_skey;   // counting sort scratch (kept across batches)
     pinned_vector<int4> h_quads;
     LineArgs largs;
     int line_grid = 0, occ_line = 0;
@@ -227,6 +228,7 @@ int long_stripe_c(const tanw_ctx *ctx, int m)
 // bytes (and no band height is forced), otherwise the tallest band that does.  0 = not even
 // kMinBandRows rows fit.
 constexpr int kMinBandRows = 32;
+constexpr int kLineKeys = 4 * (kLineMaxN + 1);      // quad sort keys: 4 strip-width classes x (n + 1)
 int long_band_rows(const tanw_ctx *ctx, int n, int m, int cf, int64_t limit)
 {
     const int64_t row_bytes = (int64_t)((m + 32 * cf - 1) / (32 * cf)) * 32 * cf;   // ptr_bytes = row_bytes*(rows+32)
@@ -487,6 +489,10 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     HostTimer host_timer;
+    static const bool trace_phases = getenv("TANW_DEBUG_PREP") != nullptr;      // host-side tuning only
+    auto mark = [&](const char *what) {
+        if (trace_phases) fprintf(stderr, "[tanw prepare] %-28s %.3f ms\n", what, host_timer.ms());
+    };
     ctx->prepared = false;
     ctx->ran = false;
     if (n_pairs < 0 || symbols_len < 0) return fail(ctx, TANW_E_INVALID, "negative size");
@@ -508,12 +514,15 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
     if (symbols_len > 0)
         TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sym.p, symbols, (size_t)symbols_len, cudaMemcpyHostToDevice, ctx->stream));
 
+    mark("symbol upload issued");
     // ---- pair table, canonical op layout, size statistics --------------------------------
     ctx->h_pairs.resize((size_t)n_pairs);
     ctx->h_ops_off.resize((size_t)n_pairs);
     ctx->h_long.clear();
     ctx->h_long_geo.clear();
     ctx->h_line.clear();
+    ctx->h_line_key.clear();
+    ctx->h_line_count.assign((size_t)kLineKeys + 1, 0);
     int64_t limit = ctx->arena_limit;
     if (limit == 0) limit = ctx->total_mem / 10 * 4;     // no cudaMemGetInfo on the per-batch path
     int64_t max_line_slot = 0, max_ck = 0;
@@ -556,9 +565,14 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
             max_long_pass = std::max<int>(max_long_pass, (int)npass);
             max_ck = std::max(max_ck, (bands - 1) * 3 * mp);
         } else if (ctx->use_lines && mp <= kLineMaxM && np <= kLineMaxN) {
-            // short pair: 8 lanes per pair, four pairs per warp
+            // short pair: 8 lanes per pair, four pairs per warp.  Sort key for the quads, counted
+            // here while the pair is at hand: descending (strip-width class, n); cell-less pairs last
             ctx->h_line.push_back((int)p);
             max_line_slot = std::max<int64_t>(max_line_slot, line_ptr_bytes((int)np, (int)mp));
+            const bool act = np > 0 && mp > 0;
+            const int key = kLineKeys - 1 - ((act ? line_c((int)mp) / 4 - 1 : 0) * (kLineMaxN + 1) + (act ? (int)np : 0));
+            ctx->h_line_key.push_back(key);
+            ++ctx->h_line_count[(size_t)key + 1];
         } else {
             max_slot = std::max<int64_t>(max_slot, ptr_bytes((int)np, (int)mp));
             max_n = std::max(max_n, (int)np);
@@ -574,6 +588,7 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
             return fail(ctx, TANW_E_INVALID, "symbol code %d >= subst_k %d", maxsym, sc->subst_k);
     }
 
+    mark("pair table + range check");
     // ---- work order: largest pairs first (greedy longest-processing-time) ------------------
     ctx->h_order.clear();
     ctx->h_order.reserve((size_t)n_pairs);
@@ -588,20 +603,13 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
     // ---- quads for the line kernel: equal strip width, similar height --------------------------
     ctx->h_quads.clear();
     if (!ctx->h_line.empty()) {
-        // counting sort on (strip-width class, n) descending; pairs without cells sort last
-        const pinned_vector<PairDesc> &hp = ctx->h_pairs;
-        const int NK = 4 * (kLineMaxN + 1);
+        // counting sort on (strip-width class, n) descending; keys and counts come from the loop above
         const size_t nl = ctx->h_line.size();
-        std::vector<int> key(nl);                 // descending (class, n) -> ascending bucket
-        for (size_t i = 0; i < nl; ++i) {
-            const PairDesc &d = hp[(size_t)ctx->h_line[i]];
-            const bool act = d.n > 0 && d.m > 0;
-            key[i] = NK - 1 - ((act ? line_c(d.m) / 4 - 1 : 0) * (kLineMaxN + 1) + (act ? d.n : 0));
-        }
-        std::vector<int> count((size_t)NK + 1, 0);
-        for (size_t i = 0; i < nl; ++i) ++count[(size_t)key[i] + 1];
-        for (int b = 1; b <= NK; ++b) count[(size_t)b] += count[(size_t)b - 1];
-        std::vector<int> sorted(nl), skey(nl);
+        std::vector<int> &count = ctx->h_line_count, &sorted = ctx->h_line_sorted, &skey = ctx->h_line_skey;
+        const std::vector<int> &key = ctx->h_line_key;
+        for (int b = 1; b <= kLineKeys; ++b) count[(size_t)b] += count[(size_t)b - 1];
+        sorted.resize(nl);
+        skey.resize(nl);
         for (size_t i = 0; i < nl; ++i) {
             const int at = count[(size_t)key[i]]++;
             sorted[(size_t)at] = ctx->h_line[i];
@@ -610,13 +618,14 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         ctx->h_quads.reserve(nl / 4 + 8);
         size_t i = 0;
         while (i < nl) {
-            const int cls = (NK - 1 - skey[i]) / (kLineMaxN + 1);
+            const int cls = (kLineKeys - 1 - skey[i]) / (kLineMaxN + 1);
             int q[4] = { -1, -1, -1, -1 };
             int c = 0;
-            while (c < 4 && i < nl && (NK - 1 - skey[i]) / (kLineMaxN + 1) == cls) q[c++] = sorted[i++];
+            while (c < 4 && i < nl && (kLineKeys - 1 - skey[i]) / (kLineMaxN + 1) == cls) q[c++] = sorted[i++];
             ctx->h_quads.push_back(make_int4(q[0], q[1], q[2], q[3]));
         }
     }
+    mark("line quads");
     const int64_t n_quads = (int64_t)ctx->h_quads.size();
     const int64_t n_batch = (int64_t)ctx->h_order.size();
     if (n_batch > 1) {
@@ -643,6 +652,7 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         ctx->h_order.swap(sorted);
     }
 
+    mark("page order");
     // ---- kernel parameters ------------------------------------------------------------------
     fill_kparams(ctx->kp, sc);
     ctx->use_subst = sc->subst != nullptr;
@@ -690,6 +700,7 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         cudaGetLastError();
         return fail(ctx, TANW_E_NOMEM, "device allocation failed (arena %lld bytes)", (long long)(slots * slot_bytes));
     }
+    mark("device buffers");
     int64_t h2d = symbols_len;
     if (n_pairs > 0) {
         TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairDesc) * (size_t)n_pairs,
@@ -707,6 +718,7 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         if (rc) return rc;
     }
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d1, ctx->stream));
+    mark("table uploads issued");
 
     BatchArgs &a = ctx->args;
     a.sym = (const uint8_t *)ctx->d_sym.p;
@@ -826,13 +838,16 @@ int tanw_batch_fetch(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_
     const int64_t P = ctx->n_pairs;
     if (P > 0 && (!ops_off || !ops_len)) return fail(ctx, TANW_E_INVALID, "NULL output table");
     if (ctx->ops_total > 0 && !ops) return fail(ctx, TANW_E_INVALID, "ops is NULL");
-    bool canonical = true;
-    for (int64_t p = 0; p < P; ++p) {
-        const int64_t cap = (int64_t)ctx->h_pairs[(size_t)p].n + ctx->h_pairs[(size_t)p].m;
-        if (ops_off[p] < 0 || ops_off[p] + cap > ops_capacity)
-            return fail(ctx, TANW_E_INVALID, "pair %lld: op buffer too small (needs n+m = %lld bytes at offset %lld)",
-                        (long long)p, (long long)cap, (long long)ops_off[p]);
-        if (ops_off[p] != ctx->h_ops_off[(size_t)p]) canonical = false;
+    // the common case first: the caller uses the canonical layout (prefix sums of n+m)
+    bool canonical = P == 0 || (memcmp(ops_off, ctx->h_ops_off.data(), sizeof(int64_t) * (size_t)P) == 0 &&
+                                ctx->ops_total <= ops_capacity);
+    if (!canonical) {
+        for (int64_t p = 0; p < P; ++p) {
+            const int64_t cap = (int64_t)ctx->h_pairs[(size_t)p].n + ctx->h_pairs[(size_t)p].m;
+            if (ops_off[p] < 0 || ops_off[p] + cap > ops_capacity)
+                return fail(ctx, TANW_E_INVALID, "pair %lld: op buffer too small (needs n+m = %lld bytes at offset %lld)",
+                            (long long)p, (long long)cap, (long long)ops_off[p]);
+        }
     }
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h0, ctx->stream));
