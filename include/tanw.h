@@ -18,8 +18,9 @@
  *   - there is no CPU fallback: without an sm_100 device tanw_create fails.
  *
  * Data model (replaces the Python lists of textSeqCompare.py:13, :21-22)
- *   symbols : uint8 codes, all sequences of the batch concatenated; equal codes <=> elements
- *             that compare equal in Python (the shim interns them per pair);
+ *   symbols : uint8 codes (uint16 after tanw_set_symbol_bytes(ctx, 2)), all sequences of the
+ *             batch concatenated; equal codes <=> elements that compare equal in Python (the
+ *             shim interns them per pair);
  *   pair p  : transcript = symbols[t_off[p] .. t_off[p]+n[p]), OCR = symbols[o_off[p] .. +m[p]);
  *   ops     : per pair, the alignment columns left to right, one byte per column:
  *             0 = (T[x], O[y])  diagonal          (textSeqCompare.py:115-125)
@@ -55,7 +56,7 @@ typedef struct tanw_ctx tanw_ctx;
 /* Scoring system after the parsing of textSeqCompare.py:24-42.
  * subst == NULL : score(a,b) = (a == b) ? match : mismatch      (:31-32, :36-37)
  * subst != NULL : score(a,b) = subst[a*subst_k + b], the tabulated user callable (:27-29);
- *                 every symbol code in the batch must be < subst_k (<= 256).
+ *                 every symbol code in the batch must be < subst_k (<= 256; <= 2048 with 16-bit codes).
  * boundary_gap  : the module-level constant gap_extend that initialises row 0 / column 0
  *                 (:9, :54-59) -- NOT the call's gap parameters. */
 typedef struct tanw_scoring {
@@ -115,6 +116,12 @@ int  tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells);
  * for one warp's share of the arena take the same route.  rows > 0 forces bands of that height
  * (tests; tuning), 0 = only when needed.  Results are identical either way. */
 int  tanw_set_long_band_rows(tanw_ctx *ctx, int rows);
+/* Width of a symbol code in bytes: 1 (default) or 2.  With 2, `symbols` in the batch calls points
+ * to uint16 codes (pass the array's address), symbols_len / t_off / o_off still count symbols,
+ * and subst_k may be up to 2048.  For pairs with more than 256 distinct elements (the reference
+ * accepts any hashable, textSeqCompare.py:13-22).  Such batches run on the page kernel only (one
+ * warp per pair); a pair whose pointers exceed one warp's share of the arena is refused. */
+int  tanw_set_symbol_bytes(tanw_ctx *ctx, int bytes);
 /* Pairs with m <= 128 and n <= 4096 are aligned four per warp by the line kernel (8 lanes per
  * pair; BASELINE config 3).  enabled = 0 sends them through the page kernel instead (same
  * results; used by the tests to compare the two paths).  Default: enabled. */

@@ -175,6 +175,54 @@ def test_callable_scorer_medium(tsc, oracle):
         assert tuple(got[2]) == _end(want[2]['end'])
 
 
+def test_wide_symbol_kernel_matches_byte_kernels(tsc):
+    """16-bit symbol codes (tanw_set_symbol_bytes) run on the page kernel only; the same pairs
+    with the same codes widened to uint16 must give exactly what the byte kernels (page, line
+    and chained-stripe routes) give."""
+    from text_alignment_b200 import _native
+    pairs = [synth.c2_pair(40 + k) for k in range(5)] + [synth.c3_pair(k) for k in range(60)] + \
+            [('', 'abc'), ('abc', ''), ('', ''), ('a', 'b'), synth.make_pair(77, 700, 33, 2, 9)]
+    buf, t_off, n, o_off, m = _pack(pairs)
+    ctx = _native.Context(0)
+    try:
+        table = np.fromfunction(lambda a, b: ((a * 7 + b * 3) % 11) - 6, (256, 256)).astype(np.int32)
+        for params, subst in [(DEFAULT, None), ((5, -4, -2, -7, 0, -5, -1), None), ((7, 2, -4, 3, -1, 1, 0), None),
+                              ((0, 0, -3, -4, -1, -2, -1), table)]:
+            narrow = ctx.align_batch(buf, t_off, n, o_off, m, ctx.make_scoring(*params, subst=subst))
+            wide = ctx.align_batch(buf.astype(np.uint16), t_off, n, o_off, m, ctx.make_scoring(*params, subst=subst))
+            assert narrow[2].tolist() == wide[2].tolist()
+            assert np.array_equal(narrow[3], wide[3])
+            for k in range(len(pairs)):
+                assert np.array_equal(narrow[0][narrow[1][k]:narrow[1][k] + narrow[2][k]],
+                                      wide[0][wide[1][k]:wide[1][k] + wide[2][k]]), k
+    finally:
+        ctx.close()
+
+
+def test_more_than_256_distinct_elements(tsc):
+    """The reference takes any hashable elements (textSeqCompare.py:13-22); pairs with more than
+    256 distinct ones get 16-bit codes.  Checked against the pure-Python restatement."""
+    from oracle import py_port
+    rng = random.Random(12)
+    alphabet = [chr(0x400 + k) for k in range(500)]
+    T = [rng.choice(alphabet) for _ in range(260)]
+    O = list(T)
+    for _ in range(60):
+        O[rng.randrange(len(O))] = rng.choice(alphabet)
+    del O[40:70]
+    O[100:100] = [rng.choice(alphabet) for _ in range(35)]
+    assert len(set(T) | set(O)) > 256
+    for system in (None, [5, -4, -2, -7, 0, -5], [lambda a, b: 6 if a == b else (-1 if ord(a) % 2 == ord(b) % 2 else -5), -7, -6, -3, -1]):
+        assert tuple(tsc.perform_alignment(T, O, system)) == tuple(py_port.perform_alignment(T, O, system))
+    # non-string elements, mixed with an ordinary pair in one batch
+    T2 = [(rng.randrange(400), 'x') for _ in range(150)]
+    O2 = T2[:60] + [(rng.randrange(400), 'x') for _ in range(80)] + T2[90:]
+    got = tsc.perform_alignment_batch([(T2, O2), (list('dominus'), list('dns')), (T, O)])
+    assert tuple(got[0]) == tuple(py_port.perform_alignment(T2, O2))
+    assert (''.join(got[1][0]), ''.join(got[1][1])) == ('domi_nus', '____dns_')
+    assert tuple(got[2]) == tuple(py_port.perform_alignment(T, O))
+
+
 def test_two_char_elements_demo_shape(tsc, oracle):
     """Elements need not be characters (textSeqCompare.py:185-186)."""
     rng = random.Random(4)

@@ -69,9 +69,24 @@ def test_encode_general_elements():
     assert not enc.reflexive
 
 
-def test_too_many_symbols():
+def test_wide_alphabets_get_16_bit_codes():
+    """More than 256 distinct elements in one pair: uint16 codes (page kernel on the device);
+    a callable scorer is tabulated, which bounds the alphabet at 2048."""
+    t = [chr(0x400 + k) for k in range(300)]
+    enc = tsc._encode_pair(t, list('ab') + t[:5], need_dense=False)
+    assert enc.t_codes.dtype == np.uint16 and enc.o_codes.dtype == np.uint16
+    assert len(enc.symbols) == 302
+    assert [enc.symbols[c] for c in enc.t_codes.tolist()] == t
+    assert [enc.symbols[c] for c in enc.o_codes.tolist()] == list('ab') + t[:5]
+    # non-string elements take the dictionary path
+    enc = tsc._encode_pair([(k, k) for k in range(400)], [(3, 3), (500, 1)], need_dense=False)
+    assert enc.t_codes.dtype == np.uint16 and enc.symbols[enc.o_codes[1]] == (500, 1)
+    # narrow pairs stay 8 bits wide
+    assert tsc._encode_pair(list('abc'), [chr(0x400)], need_dense=False).t_codes.dtype == np.uint8
     with pytest.raises(ValueError):
-        tsc._encode_pair([chr(0x400 + k) for k in range(300)], list('ab'), need_dense=False)
+        tsc._encode_pair([chr(0x400 + k) for k in range(3000)], list('ab'), need_dense=True)
+    with pytest.raises(ValueError):
+        tsc._encode_pair(list(range(70000)), [1], need_dense=False)
 
 
 def test_tabulate_only_calls_needed_pairs():

@@ -50,6 +50,7 @@ SIGNATURES = {
     'tanw_set_arena_limit': (ctypes.c_int, [_VOIDP, ctypes.c_int64]),
     'tanw_set_long_threshold': (ctypes.c_int, [_VOIDP, ctypes.c_int64]),
     'tanw_set_long_band_rows': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
+    'tanw_set_symbol_bytes': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_set_line_kernel': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_align_batch': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                         ctypes.POINTER(Scoring), _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
@@ -124,6 +125,7 @@ class Context(object):
         self._h = h
         self.device = int(device)
         self._keep = None
+        self._sym_bytes = 1
 
     def close(self):
         if getattr(self, '_h', None):
@@ -159,13 +161,22 @@ class Context(object):
         when the pointer block would not fit the arena."""
         self._check(self._lib.tanw_set_long_band_rows(self._h, int(rows)))
 
+    def _symbol_width(self, symbols):
+        """Tell the library whether `symbols` holds uint8 or uint16 codes (only when it changes)."""
+        width = symbols.dtype.itemsize
+        if width != self._sym_bytes:
+            self._check(self._lib.tanw_set_symbol_bytes(self._h, width))
+            self._sym_bytes = width
+
     def set_line_kernel(self, enabled):
         """Route short pairs (m <= 128) through the four-pairs-per-warp kernel (default on)."""
         self._check(self._lib.tanw_set_line_kernel(self._h, 1 if enabled else 0))
 
     @staticmethod
     def _canon(symbols, t_off, n, o_off, m):
-        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        # uint16 codes stay 16 bits wide (pairs with more than 256 distinct elements); anything else is bytes
+        wide = isinstance(symbols, np.ndarray) and symbols.dtype == np.uint16
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint16 if wide else np.uint8)
         t_off = np.ascontiguousarray(t_off, dtype=np.int64)
         o_off = np.ascontiguousarray(o_off, dtype=np.int64)
         n = np.ascontiguousarray(n, dtype=np.int32)
@@ -202,6 +213,7 @@ class Context(object):
         """One call = H2D + fill + traceback + D2H.  Returns (ops, ops_off, ops_len, scores).
         `out` = (ops, ops_len, scores) preallocated arrays (e.g. pinned) to receive the results."""
         symbols, t_off, n, o_off, m = self._canon(symbols, t_off, n, o_off, m)
+        self._symbol_width(symbols)
         sc, keep = scoring
         P = int(n.size)
         ops_off, total = self.canonical_ops_layout(n, m)
@@ -213,7 +225,7 @@ class Context(object):
             ops = np.empty(max(total, 1), dtype=np.uint8)
             ops_len = np.zeros(max(P, 1), dtype=np.int32)
             scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
-        rc = self._lib.tanw_align_batch(self._h, _ptr(symbols, _u8p), symbols.size, _ptr(t_off, _i64p), _ptr(n, _i32p),
+        rc = self._lib.tanw_align_batch(self._h, symbols.ctypes.data_as(_u8p), symbols.size, _ptr(t_off, _i64p), _ptr(n, _i32p),
                                         _ptr(o_off, _i64p), _ptr(m, _i32p), P, ctypes.byref(sc),
                                         _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size, _ptr(ops_len, _i32p),
                                         _ptr(scores, _i32p) if want_scores else None)
@@ -223,9 +235,10 @@ class Context(object):
     # ---- three-phase form (bench.py times run() alone with the inputs resident in HBM) ----
     def prepare(self, symbols, t_off, n, o_off, m, scoring):
         symbols, t_off, n, o_off, m = self._canon(symbols, t_off, n, o_off, m)
+        self._symbol_width(symbols)
         sc, keep = scoring
         self._keep = (symbols, t_off, n, o_off, m, sc, keep)
-        self._check(self._lib.tanw_batch_prepare(self._h, _ptr(symbols, _u8p), symbols.size, _ptr(t_off, _i64p),
+        self._check(self._lib.tanw_batch_prepare(self._h, symbols.ctypes.data_as(_u8p), symbols.size, _ptr(t_off, _i64p),
                                                  _ptr(n, _i32p), _ptr(o_off, _i64p), _ptr(m, _i32p), int(n.size),
                                                  ctypes.byref(sc)))
 

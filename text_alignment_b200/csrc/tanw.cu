@@ -94,6 +94,8 @@ struct tanw_ctx {
     DevBuf d_ck;                          // row-band checkpoints: 4 ints of traceback state, then 3*m ints per band edge
     std::vector<int2> h_long_geo;         // per long pair: (stripe strip width, rows per band)
     int long_band_rows = 0;               // 0 = one band unless the pointer block exceeds the arena limit
+    int sym_bytes = 1;                    // 1: uint8 symbol codes; 2: uint16 (page kernel only)
+    int batch_sym_bytes = 1;              // width the prepared batch was uploaded with
     int64_t long_cells = int64_t(1) << 26;   // pairs with n*m >= this use the chained-pass path
     pinned_vector<PairDesc> h_pairs;
     pinned_vector<int> h_order, h_order_sorted;
@@ -227,6 +229,7 @@ int long_stripe_c(const tanw_ctx *ctx, int m)
 // Rows per band of a chained-pass pair: the whole pair when its pointer block fits `limit`
 // bytes (and no band height is forced), otherwise the tallest band that does.  0 = not even
 // kMinBandRows rows fit.
+constexpr int kMaxWideSubstK = 2048;                // substitution table side with 16-bit symbols (16 MB)
 constexpr int kMinBandRows = 32;
 constexpr int kLineKeys = 4 * (kLineMaxN + 1);      // quad sort keys: 4 strip-width classes x (n + 1)
 int long_band_rows(const tanw_ctx *ctx, int n, int m, int cf, int64_t limit)
@@ -434,6 +437,15 @@ int tanw_set_long_threshold(tanw_ctx *ctx, int64_t cells)
     return TANW_OK;
 }
 
+int tanw_set_symbol_bytes(tanw_ctx *ctx, int bytes)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    if (bytes != 1 && bytes != 2) return fail(ctx, TANW_E_INVALID, "symbol width must be 1 or 2 bytes");
+    ctx->sym_bytes = bytes;
+    ctx->prepared = false;
+    return TANW_OK;
+}
+
 int tanw_set_long_band_rows(tanw_ctx *ctx, int rows)
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
@@ -500,19 +512,22 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
     if (symbols_len > 0 && !symbols) return fail(ctx, TANW_E_INVALID, "symbols is NULL");
     if (!sc) return fail(ctx, TANW_E_INVALID, "scoring is NULL");
     if (n_pairs > 0x7fffffff) return fail(ctx, TANW_E_INVALID, "more than 2^31-1 pairs in one batch");
-    if (sc->subst && (sc->subst_k < 1 || sc->subst_k > 256))
-        return fail(ctx, TANW_E_INVALID, "subst_k must be in 1..256");
+    const int sb = ctx->sym_bytes;
+    const int max_k = sb == 1 ? 256 : kMaxWideSubstK;
+    if (sc->subst && (sc->subst_k < 1 || sc->subst_k > max_k))
+        return fail(ctx, TANW_E_INVALID, "subst_k must be in 1..%d", max_k);
 
     // ---- start the symbol upload first: it overlaps the host-side table building below (the
     // copy is asynchronous when the caller's buffer is pinned) -------------------------------
     TANW_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->d_sym.reserve((size_t)symbols_len + 16) != cudaSuccess) {
+    if (ctx->d_sym.reserve((size_t)symbols_len * (size_t)sb + 16) != cudaSuccess) {
         cudaGetLastError();
         return fail(ctx, TANW_E_NOMEM, "device allocation failed (symbols, %lld bytes)", (long long)symbols_len);
     }
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d0, ctx->stream));
     if (symbols_len > 0)
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sym.p, symbols, (size_t)symbols_len, cudaMemcpyHostToDevice, ctx->stream));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sym.p, symbols, (size_t)symbols_len * (size_t)sb,
+                                       cudaMemcpyHostToDevice, ctx->stream));
 
     mark("symbol upload issued");
     // ---- pair table, canonical op layout, size statistics --------------------------------
@@ -547,8 +562,16 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         // a page whose pointer block does not fit one warp's share of the arena goes to the
         // chained-pass path too, which can cut it into row bands
         const bool oversize = np > 0 && mp > 0 && (ptr_bytes((int)np, (int)mp) + 255) / 256 * 256 * kWarpsPerBlock > limit &&
-                              !(ctx->use_lines && mp <= kLineMaxM && np <= kLineMaxN);
-        if ((np * mp >= ctx->long_cells || tiny_batch || oversize) && ctx->long_capacity > 0) {
+                              !(sb == 1 && ctx->use_lines && mp <= kLineMaxM && np <= kLineMaxN);
+        if (sb == 2) {
+            // 16-bit symbol codes: the page kernel only (one warp per pair, any size the arena holds)
+            if (oversize)
+                return fail(ctx, TANW_E_NOMEM, "pair %lld: %lld bytes of traceback pointers per warp exceed the arena "
+                            "limit (pairs with 16-bit symbols have no striped path)", (long long)p,
+                            (long long)ptr_bytes((int)np, (int)mp));
+            max_slot = std::max<int64_t>(max_slot, ptr_bytes((int)np, (int)mp));
+            max_n = std::max(max_n, (int)np);
+        } else if ((np * mp >= ctx->long_cells || tiny_batch || oversize) && ctx->long_capacity > 0) {
             // whole-manuscript pair: one warp per column stripe, all stripes resident at once
             const int cf = long_stripe_c(ctx, (int)mp);
             const int64_t npass = (mp + 32 * cf - 1) / (32 * cf);
@@ -583,7 +606,11 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
                     "scores do not fit the int32 fixed-point representation: (n+m+2)*max|param| must be < 2^22");
     if (sc->subst) {
         int maxsym = 0;
-        for (int64_t i = 0; i < symbols_len; ++i) maxsym = std::max<int>(maxsym, symbols[i]);
+        if (sb == 1)
+            for (int64_t i = 0; i < symbols_len; ++i) maxsym = std::max<int>(maxsym, symbols[i]);
+        else
+            for (int64_t i = 0; i < symbols_len; ++i)
+                maxsym = std::max<int>(maxsym, reinterpret_cast<const uint16_t *>(symbols)[i]);
         if (symbols_len > 0 && maxsym >= sc->subst_k)
             return fail(ctx, TANW_E_INVALID, "symbol code %d >= subst_k %d", maxsym, sc->subst_k);
     }
@@ -701,7 +728,8 @@ static int prepare_impl(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbols_l
         return fail(ctx, TANW_E_NOMEM, "device allocation failed (arena %lld bytes)", (long long)(slots * slot_bytes));
     }
     mark("device buffers");
-    int64_t h2d = symbols_len;
+    int64_t h2d = symbols_len * sb;
+    ctx->batch_sym_bytes = sb;
     if (n_pairs > 0) {
         TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairDesc) * (size_t)n_pairs,
                                        cudaMemcpyHostToDevice, ctx->stream));
@@ -809,6 +837,14 @@ int tanw_batch_run(tanw_ctx *ctx)
         // tabulated scorer; general equality scorer; gap opens <= 0; gap opens <= 0 and
         // gap_extend_y == 0 (the reference's default_sys) -- see Strip in tanw_kernels.cuh
         const int threads = kWarpsPerBlock * 32;
+        if (ctx->batch_sym_bytes == 2) {
+            switch (kernel_variant(ctx)) {
+            case -1: align_pairs_kernel<true, 0, uint16_t><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+            case 2:  align_pairs_kernel<false, 2, uint16_t><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+            case 1:  align_pairs_kernel<false, 1, uint16_t><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+            default: align_pairs_kernel<false, 0, uint16_t><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
+            }
+        } else
         switch (kernel_variant(ctx)) {
         case -1: align_pairs_kernel<true, 0><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;
         case 2:  align_pairs_kernel<false, 2><<<ctx->grid, threads, 0, ctx->stream>>>(ctx->args, ctx->kp); break;

@@ -224,7 +224,7 @@ struct PassState {
     int tnext;             // transcript symbol of the row this lane computes next
     int tnext2;            // ... and of the row after that (chained stripes prefetch two steps ahead)
     int xe, cx;            // ex*i and ox - ex*i of the row this lane computes next
-    const uint8_t *tp;     // &T[i] for the next step (row i+1 reads T[i])
+    const uint8_t *tp;     // &T[i] for the next step (row i+1 reads T[i]); byte address, symbols are SYM wide
     const int2 *bp;        // &bnd[t+2]: next boundary row to prefetch
     int2 *bw;              // &bnd[i+1]: where lane 31 leaves its right edge next
     uint8_t *pst;          // pointer bytes of this lane for the next step
@@ -293,7 +293,7 @@ __device__ __forceinline__ int2 chain_take(const Chain &ch, int4 v, int base, in
 
 // One wavefront step of one pass.  GUARDED steps check whether the lane's row is inside
 // [1, n] (ramp-up / ramp-down) and capture the corner scores; steady steps do neither.
-template <int C, bool GUARDED, bool SUBST, int VAR, bool CHAINED>
+template <int C, bool GUARDED, bool SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
 __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KParams &kp,
                                           int n, int t, int lane, bool has_next,
                                           int fin_lane, int fin_k, int (&cap)[3], const Chain &ch)
@@ -326,9 +326,11 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
     if (CHAINED) {
         // a stripe has its scheduler to itself: one step does not cover the load latency
         ps.tnext = ps.tnext2;
-        if (!GUARDED || (i + 1 >= 0 && i + 1 < n)) ps.tnext2 = (int)__ldg(ps.tp + 1);   // row i+2 reads T[i+1]
+        if (!GUARDED || (i + 1 >= 0 && i + 1 < n))
+            ps.tnext2 = (int)__ldg(reinterpret_cast<const SYM *>(ps.tp) + 1);           // row i+2 reads T[i+1]
     } else {
-        if (!GUARDED || (i >= 0 && i < n)) ps.tnext = (int)__ldg(ps.tp);     // row i+1 reads T[i]
+        if (!GUARDED || (i >= 0 && i < n))
+            ps.tnext = (int)__ldg(reinterpret_cast<const SYM *>(ps.tp));     // row i+1 reads T[i]
     }
     if (!GUARDED || (i >= 1 && i <= n)) {
         unsigned pw[C / 4];
@@ -357,7 +359,7 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
     ps.y_prev = y_in;
     ps.xe += kp.ex;
     ps.cx -= kp.ex;
-    ps.tp += 1;
+    ps.tp += sizeof(SYM);
     ps.bp += 1;
     ps.bw += 1;
     ps.pst += 32 * C;
@@ -370,9 +372,9 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
 //              bnd[i] with this pass's right edge 31 steps after lane 0 consumed it.
 //   ptr      : base of this pass's pointer bytes, laid out [step t][lane][C]
 //   fin_lane, fin_k : where column m lives in this pass (or fin_lane = -1)
-template <int C, bool SUBST, int VAR, bool CHAINED>
-__device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__restrict__ T,
-                                          const uint8_t *__restrict__ O, int n, int m, int j0,
+template <int C, bool SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
+__device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restrict__ T,
+                                          const SYM *__restrict__ O, int n, int m, int j0,
                                           bool has_next, const int2 *bnd, int2 *bnd_out,
                                           uint8_t *__restrict__ ptr, int fin_lane, int fin_k,
                                           int (&cap)[3], const Chain &ch)
@@ -383,7 +385,7 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         const int c = c0 + k;
-        s.oc[k] = (c < m) ? (int)__ldg(O + c) : 0x100;       // 0x100 never equals a symbol
+        s.oc[k] = (c < m) ? (int)__ldg(O + c) : (1 << (8 * sizeof(SYM)));   // never equals a symbol
         if (SUBST && c >= m) s.oc[k] = 0;
         // row 0: M[0][j] = X[0][j] = bg*j, Y[0][j] = -inf   (textSeqCompare.py:57-60)
         const int base = kp.bg * (c + 1);
@@ -424,7 +426,7 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
         if (lane == 0 && n > 1) ps.tnext2 = (int)__ldg(T + 1);
         if (lane == 1) ps.tnext2 = (int)__ldg(T);
     }
-    ps.tp = T + (1 - lane);
+    ps.tp = reinterpret_cast<const uint8_t *>(T + (1 - lane));
     ps.xe = kp.ex * (1 - lane);                   // row i = t - lane at t = 1
     ps.cx = kp.ox - ps.xe;
     ps.pst = ptr + ((size_t)32 + lane) * C;       // step t = 1
@@ -433,16 +435,16 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const uint8_t *__re
     const int ramp_end = min(31, last_step);
     int t = 1;
     for (; t <= ramp_end; ++t)                    // ramp-up: lanes join one per step
-        pass_step<C, true, SUBST, VAR, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
+        pass_step<C, true, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
     for (; t <= n - 1; ++t)                       // steady state: every lane on a row in [1, n-1]
-        pass_step<C, false, SUBST, VAR, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
+        pass_step<C, false, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
     for (; t <= last_step; ++t)                   // ramp-down: last row, lanes leave one per step
-        pass_step<C, true, SUBST, VAR, CHAINED>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
+        pass_step<C, true, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
 }
 
-template <bool SUBST, int VAR, bool CHAINED>
-__device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const uint8_t *T,
-                                              const uint8_t *O, int n, int m, int j0,
+template <bool SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
+__device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const SYM *T,
+                                              const SYM *O, int n, int m, int j0,
                                               bool has_next, const int2 *bnd, int2 *bnd_out,
                                               uint8_t *ptr, int fin_lane, int fin_k, int (&cap)[3],
                                               const Chain &ch)
@@ -450,8 +452,8 @@ __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const ui
 #define TANW_CASE(CC)                                                                              \
     case CC:                                                                                       \
         if constexpr (CC <= kMaxC)                                                                 \
-            fill_pass<CC, SUBST, VAR, CHAINED>(kp, T, O, n, m, j0, has_next, bnd, bnd_out, ptr,     \
-                                               fin_lane, fin_k, cap, ch);                           \
+            fill_pass<CC, SUBST, VAR, CHAINED, SYM>(kp, T, O, n, m, j0, has_next, bnd, bnd_out, ptr, \
+                                                    fin_lane, fin_k, cap, ch);                      \
         break;
     switch (C) {
         TANW_CASE(4) TANW_CASE(8) TANW_CASE(12) TANW_CASE(16)
@@ -607,7 +609,9 @@ __device__ __forceinline__ int score_out(int v)
 #ifndef TANW_MINB
 #define TANW_MINB 4
 #endif
-template <bool SUBST, int VAR>
+// SYM: uint8_t symbol codes, or uint16_t for pairs with more than 256 distinct elements
+// (tanw_set_symbol_bytes); offsets in PairDesc count symbols.
+template <bool SUBST, int VAR, typename SYM = uint8_t>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
 {
@@ -626,8 +630,8 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
         const int p = a.order[idx];
         const PairDesc pd = a.pairs[p];
         const int n = pd.n, m = pd.m;
-        const uint8_t *T = a.sym + pd.t_off;
-        const uint8_t *O = a.sym + pd.o_off;
+        const SYM *T = reinterpret_cast<const SYM *>(a.sym) + pd.t_off;
+        const SYM *O = reinterpret_cast<const SYM *>(a.sym) + pd.o_off;
         int cap[3];
         // corner scores when no cell is filled (textSeqCompare.py:53-60)
         cap[0] = kp.bg * (n > 0 ? n : m);
@@ -650,7 +654,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
                 const int cc = m - 1 - j0;
                 const int fin_lane = last ? cc / C : -1;
                 const int fin_k = last ? cc % C : -1;
-                dispatch_pass<SUBST, VAR, false>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
+                dispatch_pass<SUBST, VAR, false, SYM>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
                                                  ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap,
                                                  no_chain());
                 __syncwarp();

@@ -90,8 +90,9 @@ def parse_scoring_system(scoring_system):
 # ---- list <-> packed code conversion ------------------------------------------------------------
 
 class _Encoded(object):
-    """One pair as uint8 codes.  ``symbols``: distinct elements in code order (None when the
-    codes are the elements' own code points, which needs no table)."""
+    """One pair as uint8 codes (uint16 when it has more than 256 distinct elements).
+    ``symbols``: distinct elements in code order (None when the codes are the elements' own code
+    points, which needs no table)."""
     __slots__ = ('t_codes', 'o_codes', 'symbols', 't_cp', 'o_cp', 'reflexive')
 
 
@@ -116,6 +117,22 @@ def _code_points(seq):
         return None
 
 
+MAX_SYMBOLS = 65536          # distinct elements per pair (uint16 codes)
+MAX_TABLE_SYMBOLS = 2048     # ... when the scorer is a callable (K x K table, include/tanw.h)
+
+
+def _code_dtype(distinct, tabulated):
+    """uint8 codes while they suffice; uint16 for pairs with more distinct elements (the device
+    then runs them on the page kernel only, tanw_set_symbol_bytes)."""
+    if distinct <= 256:
+        return np.uint8
+    limit = MAX_TABLE_SYMBOLS if tabulated else MAX_SYMBOLS
+    if distinct > limit:
+        raise ValueError('more than {} distinct symbols in one pair ({}); the device path cannot '
+                         'represent them'.format(limit, distinct))
+    return np.uint16
+
+
 def _encode_pair(transcript, ocr, need_dense):
     enc = _Encoded()
     enc.reflexive = True
@@ -133,11 +150,9 @@ def _encode_pair(transcript, ocr, need_dense):
             return enc
         both = np.concatenate([t_cp, o_cp])
         uniq, inv = np.unique(both, return_inverse=True)
-        if uniq.size > 256:
-            raise ValueError('more than 256 distinct symbols in one pair ({}); the uint8 device path '
-                             'cannot represent them'.format(uniq.size))
-        enc.t_codes = inv[:t_cp.size].astype(np.uint8)
-        enc.o_codes = inv[t_cp.size:].astype(np.uint8)
+        code_t = _code_dtype(uniq.size, need_dense)
+        enc.t_codes = inv[:t_cp.size].astype(code_t)
+        enc.o_codes = inv[t_cp.size:].astype(code_t)
         enc.symbols = [chr(c) for c in uniq.tolist()]
         return enc
     # general elements (e.g. the 2-character strings of the reference's demo, :185-186)
@@ -162,11 +177,9 @@ def _encode_pair(transcript, ocr, need_dense):
             return c
     t_codes = [code_of(e) for e in transcript]
     o_codes = [code_of(e) for e in ocr]
-    if len(symbols) > 256:
-        raise ValueError('more than 256 distinct symbols in one pair ({}); the uint8 device path '
-                         'cannot represent them'.format(len(symbols)))
-    enc.t_codes = np.asarray(t_codes, dtype=np.uint8)
-    enc.o_codes = np.asarray(o_codes, dtype=np.uint8)
+    code_t = _code_dtype(len(symbols), need_dense)
+    enc.t_codes = np.asarray(t_codes, dtype=code_t)
+    enc.o_codes = np.asarray(o_codes, dtype=code_t)
     enc.symbols = symbols
     # a == b must mean "same code"; objects with a non-reflexive == (NaN) break that
     for s in symbols:
@@ -290,10 +303,13 @@ def perform_alignment_batch(pairs, scoring_system=None, devices=None, return_sco
     need_table = [fn is not None or not e.reflexive for e in encs]
     results = [None] * len(pairs)
     plain = [k for k in range(len(pairs)) if not need_table[k]]
-    if plain:
-        out = _run_group([encs[k] for k in plain], (match, mismatch, gox, goy, gex, gey, boundary), None, devices)
-        for k, r in zip(plain, out):
-            results[k] = r
+    # pairs with 16-bit codes run on the page kernel only: keep them out of the others' launch
+    for group in ([k for k in plain if encs[k].t_codes.dtype == np.uint8],
+                  [k for k in plain if encs[k].t_codes.dtype != np.uint8]):
+        if group:
+            out = _run_group([encs[k] for k in group], (match, mismatch, gox, goy, gex, gey, boundary), None, devices)
+            for k, r in zip(group, out):
+                results[k] = r
     for k in range(len(pairs)):
         if need_table[k]:
             # a substitution table is specific to the pair's symbol set: one launch per pair
@@ -404,7 +420,7 @@ def split_by_cells(n, m, parts):
 
 
 def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, want_scores=True):
-    """Packed-buffer entry: uint8 codes + offsets in, op strings out (include/tanw.h layout).
+    """Packed-buffer entry: uint8 (or uint16) codes + offsets in, op strings out (include/tanw.h layout).
 
     params = (match, mismatch, gap_open_x, gap_open_y, gap_extend_x, gap_extend_y, boundary_gap).
     devices: list of CUDA device indices; the batch is cut into contiguous, cell-balanced
@@ -412,7 +428,8 @@ def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, 
     if devices is None:
         devices = [0]
     devices = list(devices)
-    symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+    wide = isinstance(symbols, np.ndarray) and symbols.dtype == np.uint16
+    symbols = np.ascontiguousarray(symbols, dtype=np.uint16 if wide else np.uint8)
     t_off = np.ascontiguousarray(t_off, dtype=np.int64)
     o_off = np.ascontiguousarray(o_off, dtype=np.int64)
     n = np.ascontiguousarray(n, dtype=np.int32)
