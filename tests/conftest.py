@@ -58,5 +58,15 @@ def random_pairs():
 
 
 @pytest.fixture(scope='session')
+def wide_pairs():
+    """Pairs with more than 256 distinct elements; T / O are stored as code points."""
+    recs = load_golden('wide_pairs.json')
+    for r in recs:
+        r['T'] = [chr(c) for c in r['T']]
+        r['O'] = [chr(c) for c in r['O']]
+    return recs
+
+
+@pytest.fixture(scope='session')
 def appendix_c():
     return load_golden('appendix_c.json')

@@ -210,9 +210,38 @@ def consumer_golden():
     json.dump(dict(pages=pages, syllables=syl), open(os.path.join(HERE, 'consumer.json'), 'w'), indent=0)
 
 
+def wide_golden():
+    """Pairs with more than 256 distinct elements (16-bit symbol codes on the device).  Elements
+    are single characters drawn from a large alphabet, stored as code points."""
+    rng = random.Random(20261018)
+    out = []
+    for n, m, k_alpha, system in [(260, 320, 3000, None), (200, 330, 2500, [5, -4, -2, -7, 0, -5]),
+                                  (300, 220, 2000, [10, -5, -7, -7]), (180, 420, 1500, ['asymmetric', -3, -3, -1, -1])]:
+        alphabet = [chr(0x100 + c) for c in range(k_alpha)]        # no '_' (gap symbol), no ' '
+        T = [rng.choice(alphabet) for _ in range(n)]
+        O = list(T)
+        for _ in range(n // 4):
+            O[rng.randrange(len(O))] = rng.choice(alphabet)
+        cut = rng.randrange(0, max(1, len(O) - 20))
+        del O[cut:cut + 15]
+        while len(O) < m:
+            at = rng.randrange(0, len(O) + 1)
+            O[at:at] = [rng.choice(alphabet) for _ in range(min(m - len(O), rng.randint(1, 25)))]
+        O = O[:m]
+        assert len(set(T) | set(O)) > 256
+        r = run_ref(T, O, system)
+        out.append(dict(T=[ord(c) for c in T], O=[ord(c) for c in O], system=system, ops=r['ops'], end=r['end'],
+                        ptr_sha256=r['ptr_sha256']))
+        print('wide', n, m, len(set(T) | set(O)), r['end'], len(r['ops']))
+    json.dump(out, open(os.path.join(HERE, 'wide_pairs.json'), 'w'), indent=0)
+
+
 if __name__ == '__main__':
     if '--only-consumer' in sys.argv:
         consumer_golden()
+    elif '--only-wide' in sys.argv:
+        wide_golden()
     else:
         main()
         consumer_golden()
+        wide_golden()

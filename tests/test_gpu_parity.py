@@ -85,6 +85,15 @@ def test_random_golden_pairs(tsc, random_pairs):
             assert tuple(score) == _end(rec['end']), (rec['T'], rec['O'], rec['system'])
 
 
+def test_wide_alphabet_golden_pairs(tsc, wide_pairs):
+    """Vectors of the unmodified reference on pairs with more than 256 distinct elements
+    (16-bit symbol codes, incl. a callable scorer over 409 symbols)."""
+    for rec in wide_pairs:
+        tra, ocr, score = tsc.perform_alignment(rec['T'], rec['O'], resolve_system(rec['system']), return_scores=True)
+        assert ops_string(tra, ocr) == rec['ops'], rec['system']
+        assert tuple(score) == _end(rec['end']), rec['system']
+
+
 def test_appendix_c_pages(tsc, appendix_c):
     """The three seeded page/line vectors of SURVEY.md Appendix C (digests from the reference)."""
     for rec in appendix_c:

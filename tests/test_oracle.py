@@ -64,6 +64,20 @@ def test_py_port_golden(kats, random_pairs):
         assert hashlib.sha256(np.ascontiguousarray(ptr).tobytes()).hexdigest() == rec['ptr_sha256']
 
 
+def test_py_port_wide_alphabet_golden(wide_pairs):
+    """Vectors of the unmodified reference on pairs with 326-409 distinct elements (the C oracle
+    is limited to 256 codes; the Python port is the checker for the 16-bit device path)."""
+    for rec in wide_pairs:
+        T, O = rec['T'], rec['O']
+        tra, ocr, full = py_port.perform_alignment(T, O, resolve_system(rec['system']), full=True)
+        assert ''.join(map(str, full['ops'])) == rec['ops']
+        end = [full[k][len(T)][len(O)] for k in ('M', 'X', 'Y')]
+        assert _end_ints(end) == rec['end']
+        ptr = (full['PM'].astype(np.uint8) | (full['PX'].astype(np.uint8) << 2) |
+               (full['PY'].astype(np.uint8) << 4))[1:, 1:]
+        assert hashlib.sha256(np.ascontiguousarray(ptr).tobytes()).hexdigest() == rec['ptr_sha256']
+
+
 def test_c_oracle_appendix_c(appendix_c):
     for rec in appendix_c:
         t, o = synth.make_pair(rec['seed'], rec['n'], rec['m'], rec['run_lo'], rec['run_hi'])
