@@ -703,7 +703,8 @@ constexpr int kLineG = 8;
 constexpr int kLineMaxC = 16;
 constexpr int kLineMaxM = kLineG * kLineMaxC;      // 128 columns
 constexpr int kLineMaxN = 4096;                    // bounds the per-group pointer slot
-constexpr int kLineTile = 2 * kLineMaxC / 4 + 1;   // words per tile row (two strips + pad)
+constexpr int kLineTile = 2 * kLineMaxC / 4 + 1;   // words per tile row (guard word + two strips)
+constexpr unsigned kLineSentinel = 0x80808080u;
 
 __host__ __device__ inline int line_c(int m) { return m <= 0 ? 4 : ((m + 31) / 32) * 4; }
 __host__ __device__ inline long long line_ptr_bytes(int n, int m)
@@ -762,14 +763,25 @@ template <int C>
 __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m, bool act,
                                                 uint8_t *ops_end, unsigned *tile, int gl)
 {
+    // Tile of a group: 8 rows (row r = matrix row x - r) plus a guard row; every row is a guard
+    // word followed by the DECODED pointer bytes of two strips.  The walk is 3.6 % of the page
+    // kernel's instructions but 12 % of this kernel's (a tile is only eight rows high), so its
+    // loop is kept to eleven instructions:
+    //   pointer byte b = tagM | tagX << 2 | tagY << 4 (tags 2 / 1 / 0 = came from M / X / Y);
+    //   walk state st = 2 - tag (0 diagonal, 1 x-gap, 2 y-gap; :110-145), kept as s = 2*st;
+    //   decoded byte d = (0x2A - b) << 1 holds 2*(2 - tag) per field: next state s' = (d >> s) & 6;
+    //   guard bytes are 0x80 (a decoded byte is at most 0x54) and end the walk instead of row /
+    //   column counters; the move (+35 diagonal, +36 up, -1 left) is one byte permute on s.
     int x = n, y = m, k = 0, st = -1;
+    tile[kLineG * kLineTile + gl] = kLineSentinel;           // guard row: words 0..7 ...
+    if (gl == 0) tile[kLineG * kLineTile + kLineG] = kLineSentinel;                 // ... and 8
     while (__any_sync(kFull, act && x > 0 && y > 0)) {
         const bool mine = act && x > 0 && y > 0;
         const int sidx = mine ? (y - 1) / C : 0;             // strip that holds column y
         const int row = x - gl;
         unsigned w[2 * C / 4];
 #pragma unroll
-        for (int q = 0; q < 2 * C / 4; ++q) w[q] = 0;
+        for (int q = 0; q < 2 * C / 4; ++q) w[q] = 0xFFFFFFFFu;     // outside the matrix (no pointer word is all ones)
         if (mine && row >= 1) {
             const unsigned *hi = reinterpret_cast<const unsigned *>(ptr + ((size_t)(row + sidx) * kLineG + sidx) * C);
 #pragma unroll
@@ -781,28 +793,34 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
             }
         }
         __syncwarp();
+        tile[gl * kLineTile] = kLineSentinel;
 #pragma unroll
-        for (int q = 0; q < 2 * C / 4; ++q) tile[gl * kLineTile + q] = w[q];
+        for (int q = 0; q < 2 * C / 4; ++q)
+            tile[gl * kLineTile + 1 + q] = (w[q] == 0xFFFFFFFFu) ? kLineSentinel : (0x2A2A2A2Au - (w[q] & 0x3F3F3F3Fu)) << 1;
         __syncwarp();
         if (mine && gl == 0) {
             const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
-            const int col0 = (sidx - 1) * C;                 // 0-based column of the window start
-            int off = (y - 1) - col0;                        // row 0 of the window, C .. 2C-1
-            if (st < 0) st = 2 - (int)(tb[off] & 3u);                                 // :102
-            const int xr0 = min(x, kLineG), yr0 = min(y, off + 1);
-            int xr = xr0, yr = yr0;
-            while (xr > 0 && yr > 0) {                                                // :115-145
-                const unsigned b = tb[off];
-                const int dx = (st != 2), dy = (st != 1);
-                ++k;
-                *(ops_end - k) = (uint8_t)st;
-                off += dx * (kLineTile * 4) - dy;
-                xr -= dx;
-                yr -= dy;
-                st = 2 - (int)((b >> (2 * st)) & 3u);
+            const int col0 = (sidx - 1) * C;                 // 0-based column of the first data byte
+            int off = 4 + (y - 1) - col0;                    // row 0 of the window
+            unsigned d = tb[off];
+            int s = 2 * st;
+            if (st < 0) s = (int)(d & 6u);                   // state from mat_ptr first          (:102)
+            uint8_t *op = ops_end - k;
+            const uint8_t *const op0 = op;
+            while (!(d & 0x80u)) {                                                        // :115-145
+                *--op = (uint8_t)(s >> 1);
+                int delta;                                   // byte s of {35, 0, 36, 0, -1, -1}, byte s+1 its sign extension
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(delta)
+                    : "r"(0x00240023), "r"(0x0000FFFF), "r"(s * 0x1111 + 0x1110));
+                off += delta;
+                s = (int)((d >> s) & 6u);
+                d = tb[off];
             }
-            x -= xr0 - xr;
-            y -= yr0 - yr;
+            k += (int)(op0 - op);
+            const int r = off / (kLineTile * 4);
+            x -= r;
+            y = col0 + (off - r * (kLineTile * 4)) - 3;
+            st = s >> 1;
         }
         x = __shfl_sync(kFull, x, 0, kLineG);
         y = __shfl_sync(kFull, y, 0, kLineG);
@@ -914,13 +932,13 @@ template <bool SUBST, int VAR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
 {
-    __shared__ unsigned tiles[kWarpsPerBlock][4 * kLineG * kLineTile];
+    __shared__ unsigned tiles[kWarpsPerBlock][4 * (kLineG + 1) * kLineTile];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane >> 3;
     const long long slot = ((long long)blockIdx.x * kWarpsPerBlock + warp) * 4 + g;
     uint8_t *const ptr = a.ptr_arena + (size_t)slot * (size_t)a.slot_bytes;
-    unsigned *const tile = tiles[warp] + g * (kLineG * kLineTile);
+    unsigned *const tile = tiles[warp] + g * ((kLineG + 1) * kLineTile);
     for (;;) {
         unsigned idx = 0;
         if (lane == 0) idx = atomicAdd(a.counter, 1u);
