@@ -510,6 +510,7 @@ struct PtrCursor {
     }
 };
 
+constexpr unsigned kGuardWord = 0x80808080u;       // four guard bytes: end a guarded traceback walk
 constexpr int kTileRows = 64;                      // rows of a traceback tile (two per lane)
 constexpr int kTileWords = 16;                     // 64 columns of a traceback tile
 constexpr int kTileStride = kTileWords + 1;        // words per tile row in shared memory (+ pad)
@@ -583,6 +584,90 @@ __device__ __forceinline__ void traceback_core(const uint8_t *ptr, int n, int m,
     }
 }
 
+// The same walk for the batched page kernel, where the one-lane loop costs issue slots that the
+// other warps of the scheduler could use (3.5 % of the kernel's instructions): guarded tile,
+// decoded bytes and a permute-based move as in traceback_groups -- 13 instructions per path step
+// instead of 25 (+0.9 % on config 2).  The lone warp of a chained pair keeps traceback_core: there
+// the loop branch of this form has to wait for each step's own load (measured 5 % slower).
+// `tile` needs (kTileRows + 1) * kTileStride words.
+__device__ __forceinline__ void traceback_core_guarded(const uint8_t *ptr, int n, int m, int cfull,
+                                               uint8_t *ops_end, unsigned *tile, int lane,
+                                               int &x, int &y, int &st, int &k)
+{
+    const PtrMap map(n, m, cfull);
+    if (lane < kTileStride) tile[kTileRows * kTileStride + lane] = kGuardWord;       // guard row above the tile
+    while (x > 0 && y > 0) {
+        // ---- tile load: word columns wq_hi-15 .. wq_hi, rows x-lane and x-32-lane ----------
+        const int wq_hi = (y - 1) >> 2;
+        const int row0 = x - lane, row1 = x - 32 - lane;
+        unsigned w0[kTileWords], w1[kTileWords];
+        PtrCursor cur;
+        cur.seek(map, wq_hi);
+#pragma unroll
+        for (int q = kTileWords - 1; q >= 0; --q) {
+            const int wq = wq_hi - (kTileWords - 1 - q);
+            // outside the matrix: becomes a guard word (no pointer word is all ones: tags are <= 2).
+            // Nothing here may consume a loaded value, or the 32 loads of a lane would serialise.
+            w0[q] = 0xFFFFFFFFu; w1[q] = 0xFFFFFFFFu;
+            if (wq >= 0) {
+                if (row0 >= 1) w0[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row0)));
+                if (row1 >= 1) w1[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row1)));
+                if (wq > 0) cur.left(map);
+            }
+        }
+        __syncwarp();
+        // Tile row r = matrix row x - r: one guard word, then 16 words of DECODED bytes.
+        //   pointer byte b = tagM | tagX << 2 | tagY << 4 (tags 2 / 1 / 0 = came from M / X / Y);
+        //   walk state st = 2 - tag (0 diagonal, 1 x-gap, 2 y-gap; :110-145), kept as s = 2*st;
+        //   decoded byte d = (0x2A - b) << 1 holds 2*(2 - tag) per field: next state s' = (d >> s) & 6;
+        //   guard bytes are 0x80 (a decoded byte is at most 0x54): the walk stops on them.
+        tile[lane * kTileStride] = kGuardWord;
+        tile[(lane + 32) * kTileStride] = kGuardWord;
+#pragma unroll
+        for (int q = 0; q < kTileWords; ++q) {
+            tile[lane * kTileStride + 1 + q] =
+                (w0[q] == 0xFFFFFFFFu) ? kGuardWord : (0x2A2A2A2Au - (w0[q] & 0x3F3F3F3Fu)) << 1;
+            tile[(lane + 32) * kTileStride + 1 + q] =
+                (w1[q] == 0xFFFFFFFFu) ? kGuardWord : (0x2A2A2A2Au - (w1[q] & 0x3F3F3F3Fu)) << 1;
+        }
+        __syncwarp();
+        // ---- walk inside the tile ---------------------------------------------------------
+        // The move comes out of a byte permute on the state (+67 diagonal, +68 up, -1 left in a
+        // tile of 68-byte rows) and the guards replace the row / column counters.
+        const int col_lo = (wq_hi - (kTileWords - 1)) * 4;          // 0-based column of the first data byte
+        int cnt = 0;
+        if (lane == 0) {
+            const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
+            int off = 4 + (y - 1) - col_lo;                         // row 0 of the tile
+            unsigned d = tb[off];
+            int s = 2 * st;
+            if (st < 0) s = (int)(d & 6u);                          // state from mat_ptr first   (:102)
+            uint8_t *op = ops_end - k;                              // ops go out back to front
+            while (!(d & 0x80u)) {
+                *--op = (uint8_t)(s >> 1);
+                ++cnt;
+                // byte s of {67, 0, 68, 0, -1, -1} with byte s+1 as its sign extension
+                // (prmt directly: __byte_perm would first mask the selector, one more op on the chain)
+                int delta;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(delta)
+                    : "r"(0x00440043), "r"(0x0000FFFF), "r"(s * 0x1111 + 0x1110));
+                off += delta;
+                s = (int)((d >> s) & 6u);
+                d = tb[off];
+            }
+            const int r = off / (kTileStride * 4);
+            x -= r;
+            y = col_lo + (off - r * (kTileStride * 4)) - 3;
+            st = s >> 1;
+        }
+        x = __shfl_sync(kFull, x, 0);
+        y = __shfl_sync(kFull, y, 0);
+        st = __shfl_sync(kFull, st, 0);
+        cnt = __shfl_sync(kFull, cnt, 0);
+        k += cnt;
+    }
+}
+
 // Traceback of one pair (textSeqCompare.py:96-164) by one warp.  The pointer chase is a chain
 // of dependent loads, so the warp first pulls the 64-row x 64-column tile of pointer bytes
 // whose bottom-right corner is the current cell into shared memory (lane r: rows x-r and
@@ -593,7 +678,7 @@ __device__ __forceinline__ int traceback_warp(const uint8_t *ptr, int n, int m, 
                                               uint8_t *ops_end, unsigned *tile, int lane)
 {
     int x = n, y = m, k = 0, st = -1;
-    if (n > 0 && m > 0) traceback_core(ptr, n, m, cfull, ops_end, tile, lane, x, y, st, k);
+    if (n > 0 && m > 0) traceback_core_guarded(ptr, n, m, cfull, ops_end, tile, lane, x, y, st, k);
     if (lane == 0) {
         while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // OCR remainder first       (:154-158)
         while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // then transcript remainder (:160-164)
@@ -615,7 +700,7 @@ template <bool SUBST, int VAR, typename SYM = uint8_t>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
 {
-    __shared__ unsigned tiles[kWarpsPerBlock][kTileRows * kTileStride];
+    __shared__ unsigned tiles[kWarpsPerBlock][(kTileRows + 1) * kTileStride];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * kWarpsPerBlock + warp;
@@ -704,7 +789,6 @@ constexpr int kLineMaxC = 16;
 constexpr int kLineMaxM = kLineG * kLineMaxC;      // 128 columns
 constexpr int kLineMaxN = 4096;                    // bounds the per-group pointer slot
 constexpr int kLineTile = 2 * kLineMaxC / 4 + 1;   // words per tile row (guard word + two strips)
-constexpr unsigned kLineSentinel = 0x80808080u;
 
 __host__ __device__ inline int line_c(int m) { return m <= 0 ? 4 : ((m + 31) / 32) * 4; }
 __host__ __device__ inline long long line_ptr_bytes(int n, int m)
@@ -773,8 +857,8 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
     //   guard bytes are 0x80 (a decoded byte is at most 0x54) and end the walk instead of row /
     //   column counters; the move (+35 diagonal, +36 up, -1 left) is one byte permute on s.
     int x = n, y = m, k = 0, st = -1;
-    tile[kLineG * kLineTile + gl] = kLineSentinel;           // guard row: words 0..7 ...
-    if (gl == 0) tile[kLineG * kLineTile + kLineG] = kLineSentinel;                 // ... and 8
+    tile[kLineG * kLineTile + gl] = kGuardWord;           // guard row: words 0..7 ...
+    if (gl == 0) tile[kLineG * kLineTile + kLineG] = kGuardWord;                 // ... and 8
     while (__any_sync(kFull, act && x > 0 && y > 0)) {
         const bool mine = act && x > 0 && y > 0;
         const int sidx = mine ? (y - 1) / C : 0;             // strip that holds column y
@@ -793,10 +877,10 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
             }
         }
         __syncwarp();
-        tile[gl * kLineTile] = kLineSentinel;
+        tile[gl * kLineTile] = kGuardWord;
 #pragma unroll
         for (int q = 0; q < 2 * C / 4; ++q)
-            tile[gl * kLineTile + 1 + q] = (w[q] == 0xFFFFFFFFu) ? kLineSentinel : (0x2A2A2A2Au - (w[q] & 0x3F3F3F3Fu)) << 1;
+            tile[gl * kLineTile + 1 + q] = (w[q] == 0xFFFFFFFFu) ? kGuardWord : (0x2A2A2A2Au - (w[q] & 0x3F3F3F3Fu)) << 1;
         __syncwarp();
         if (mine && gl == 0) {
             const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
