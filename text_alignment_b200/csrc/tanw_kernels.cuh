@@ -365,6 +365,9 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
     ps.pst += 32 * C;
 }
 
+#ifndef TANW_STEADY_UNROLL2
+#define TANW_STEADY_UNROLL2 1
+#endif
 // One pass: columns [j0, j0 + 32*C) of one pair, all n rows.
 //   bnd      : bnd[i], i = 1..n: (Q, Y) of the column left of the pass, row i -- column 0 of
 //              the matrices for the first pass (written by the caller, textSeqCompare.py:53-56),
@@ -436,7 +439,18 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restri
     int t = 1;
     for (; t <= ramp_end; ++t)                    // ramp-up: lanes join one per step
         pass_step<C, true, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
-    for (; t <= n - 1; ++t)                       // steady state: every lane on a row in [1, n-1]
+    // steady state: every lane on a row in [1, n-1].  Two steps per iteration in the batched
+    // kernel: the strip state (D, X^, W per column) otherwise ends every step in other registers
+    // than the next one expects, and 27 of the 252 instructions of a C = 16 step were moves.
+    if (!CHAINED && TANW_STEADY_UNROLL2) {
+#pragma unroll 1
+        for (; t + 1 <= n - 1; t += 2) {
+            pass_step<C, false, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
+            pass_step<C, false, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t + 1, lane, has_next, fin_lane, fin_k, cap, ch);
+        }
+    }
+#pragma unroll 1
+    for (; t <= n - 1; ++t)
         pass_step<C, false, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
     for (; t <= last_step; ++t)                   // ramp-down: last row, lanes leave one per step
         pass_step<C, true, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
