@@ -368,6 +368,9 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
 #ifndef TANW_STEADY_UNROLL2
 #define TANW_STEADY_UNROLL2 1
 #endif
+#ifndef TANW_CHAINED_UNROLL2
+#define TANW_CHAINED_UNROLL2 1
+#endif
 // One pass: columns [j0, j0 + 32*C) of one pair, all n rows.
 //   bnd      : bnd[i], i = 1..n: (Q, Y) of the column left of the pass, row i -- column 0 of
 //              the matrices for the first pass (written by the caller, textSeqCompare.py:53-56),
@@ -442,7 +445,7 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restri
     // steady state: every lane on a row in [1, n-1].  Two steps per iteration in the batched
     // kernel: the strip state (D, X^, W per column) otherwise ends every step in other registers
     // than the next one expects, and 27 of the 252 instructions of a C = 16 step were moves.
-    if (!CHAINED && TANW_STEADY_UNROLL2) {
+    if ((!CHAINED || TANW_CHAINED_UNROLL2) && TANW_STEADY_UNROLL2) {
 #pragma unroll 1
         for (; t + 1 <= n - 1; t += 2) {
             pass_step<C, false, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
@@ -987,7 +990,14 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
         int t = 1;
         for (; t <= min(kLineG - 1, last_step); ++t)         // ramp-up
             line_step<C, true, SUBST, VAR>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
-        for (; t <= nmin - 1; ++t)                           // every lane of every group on a row in [1, n-1]
+        // every lane of every group on a row in [1, n-1]; two steps per iteration (see fill_pass)
+#pragma unroll 1
+        for (; t + 1 <= nmin - 1; t += 2) {
+            line_step<C, false, SUBST, VAR>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
+            line_step<C, false, SUBST, VAR>(s, ls, kp, n, act, t + 1, gl, fin_lane, fin_k, cap);
+        }
+#pragma unroll 1
+        for (; t <= nmin - 1; ++t)
             line_step<C, false, SUBST, VAR>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
         for (; t <= last_step; ++t)                          // ramp-down and the taller pairs' tails
             line_step<C, true, SUBST, VAR>(s, ls, kp, n, act, t, gl, fin_lane, fin_k, cap);
