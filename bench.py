@@ -46,7 +46,7 @@ def ncu_traffic(workload, npairs):
     committed ncu --set full summary of the same workload (profiles/); None if it does not apply."""
     if workload != 'c2' or npairs != WORKLOADS['c2']['default_pairs']:
         return None
-    path = os.path.join(ROOT, 'profiles', 'r1k_align_pairs_ncu.txt')
+    path = os.path.join(ROOT, 'profiles', 'r1m_align_pairs_ncu.txt')
     scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
     total = 0.0
     try:
