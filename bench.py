@@ -2,29 +2,35 @@
 """bench.py -- headline benchmark of the affine-gap NW hot path (BASELINE.json `metric`).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c3|c4] [--pairs P]
+                    [--workload c1|c2|c3|c4|c5] [--pairs P] [--no-others] [--no-sharded]
 
 A "step" is one pass of the hot path over one batch: `--pairs` synthetic pairs of the chosen
 BASELINE config per GPU (default config 2: 10 000 seeded page pairs of 1-2k characters;
 SURVEY.md 8(d)), default scoring [8,-4,-7,-7,-3,0].  Weak scaling: every rank aligns its own
 batch, no data-path collective (pairs are independent).
 
-  value  : whole-job GCUPS (sum over ranks of n*m / max-over-ranks device time), inputs
-           resident in HBM, timed with CUDA events on the library's stream;
-  e2e    : the same metric through the C-ABI call tanw_align_batch with pinned HOST buffers:
-           H2D of symbols + pair table, fill, traceback, D2H of op strings / lengths / scores
-           inside the timed region;
+  value    : whole-job GCUPS (sum over ranks of n*m / max-over-ranks device time), inputs
+             resident in HBM, timed with CUDA events on the library's stream;
+  e2e      : the same metric through the C-ABI call tanw_align_batch with pinned HOST buffers:
+             H2D of symbols + pair table, fill, traceback, D2H of op strings / lengths / scores
+             inside the timed region;
+  others   : the other four BASELINE configs (c1, c3, c4, c5) measured the same way with a
+             short step count, so that the driver's record carries every config;
+  sharded  : (--gpus N > 1) the product's own in-process multi-GPU entry
+             align_packed(devices=range(N)) timed by rank 0 on one N x batch (weak) and on one
+             single batch (strong scaling), gather checked bit-exact against the per-rank results;
   roofline / cpu_baseline : see DESIGN.md "Measurement".
 
-`--impl reference` times the CPU restatement of the reference's pure-Python aligner
-(oracle/py_port.py; the reference itself, being Python, cannot travel to the GPU box) over
-all host cores on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference aligner (oracle/_ref/textSeqCompare.py, copied
+byte for byte from /root/reference by `make -C oracle ref`; the pure-Python restatement
+oracle/py_port.py only if that copy is absent) over all host cores on a bounded sample of the
+same workload.
 """
 import argparse
+import hashlib
 import json
 import multiprocessing as mp
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -41,22 +47,34 @@ DEFAULT_PARAMS = (8, -4, -7, -7, -3, 0, -1)
 NOMINAL_INT32_PEAK = 148 * 64 * 1.965e9     # alu pipe, lane-ops/s
 
 
+def source_digest():
+    """Digest of the kernel sources: ncu-derived figures (profiles/traffic.json) are only quoted
+    while they describe the build that is being timed."""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, 'text_alignment_b200', 'csrc')
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith(('.cu', '.cuh', '.h')):
+            with open(os.path.join(csrc, name), 'rb') as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(workload, npairs):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-    committed ncu --set full summary of the same workload (profiles/); None if it does not apply."""
-    if workload != 'c2' or npairs != WORKLOADS['c2']['default_pairs']:
-        return None
-    path = os.path.join(ROOT, 'profiles', 'r1m_align_pairs_ncu.txt')
-    scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
-    total = 0.0
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of this
+    workload from profiles/traffic.json (written by tools/ncu_summary.py from one
+    `ncu --set full` capture); None when no capture of this workload and size exists.  The
+    entry names the source digest it was captured on (`stale` when the kernels changed since)."""
     try:
-        for line in open(path):
-            f = line.split()
-            if len(f) >= 3 and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-                total += float(f[2]) * scale.get(f[1], 1.0)
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            tab = json.load(f)
     except (OSError, ValueError):
-        return None
-    return total or None
+        return None, None
+    ent = tab.get(workload)
+    if not ent or int(ent.get('pairs', -1)) != int(npairs):
+        return None, None
+    note = dict(source=ent.get('source'), kernel=ent.get('kernel'),
+                stale=ent.get('digest') != source_digest())
+    return float(ent['dram_bytes_per_launch']), note
 
 
 def measured_peaks():
@@ -113,6 +131,12 @@ WORKLOADS = {
     'c5': dict(name='config 5: whole-manuscript pair, seed 5001, n=80000 x m=100000 (chained-pass path)',
                default_pairs=1),
 }
+
+
+def base_config(which, npairs, cells, world):
+    """The `config` object: identical keys in both arms (ours / reference)."""
+    return dict(workload=WORKLOADS[which]['name'], pairs_per_gpu=int(npairs), cells_per_gpu=int(cells),
+                scoring=list(DEFAULT_PARAMS[:6]), parallelism='pairs sharded, %d rank(s)' % world)
 
 
 # ---- clocks ----------------------------------------------------------------------------------
@@ -183,34 +207,51 @@ class ClockSampler(object):
                     samples=len(inside), reasons=reasons, how='NVML, %d ms period' % int(self.period * 1e3))
 
 
-# ---- CPU baseline (oracle: the only place bench.py may execute oracle/) -------------------------
+# ---- CPU arms (the only places bench.py may execute oracle/) ------------------------------------
 
-def _py_port_one(args):
+def cpu_aligner():
+    """(perform_alignment, kind, what): the unmodified reference when oracle/_ref holds its
+    byte-identical copy, else the pure-Python restatement."""
+    from oracle import ref_copy
+    if ref_copy.available():
+        return (ref_copy.load().perform_alignment, 'reference',
+                'UNMODIFIED /root/reference/textSeqCompare.py perform_alignment (oracle/_ref copy, sha256 %s...)'
+                % ref_copy.EXPECTED_SHA256[:12])
     from oracle import py_port
+    return (py_port.perform_alignment, 'port',
+            'pure-Python restatement of textSeqCompare.py (oracle/py_port.py; oracle/_ref absent)')
+
+
+def _cpu_one(args):
+    fn = cpu_aligner()[0]
     t, o = args
     t0 = time.perf_counter()
-    py_port.perform_alignment(list(t), list(o))
+    fn(list(t), list(o))
     return len(t) * len(o), time.perf_counter() - t0
 
 
 def crop_pairs(pairs, cells_per_pair):
+    """Pairs cut to about cells_per_pair cells (both strings shortened by the same factor);
+    pairs that are already smaller stay whole."""
     out = []
+    whole = True
     for t, o in pairs:
         f = min(1.0, (cells_per_pair / max(1.0, float(len(t)) * len(o))) ** 0.5)
+        whole = whole and f >= 1.0
         out.append((t[:max(1, int(len(t) * f))], o[:max(1, int(len(o) * f))]))
-    return out
+    return out, whole
 
 
-def cpu_python_port(pairs, cores, target_s):
-    """The reference's algorithm in pure Python (oracle/py_port.py, ~10 us per cell like the
-    reference), one pair per host core, pairs cropped so a step lasts about target_s."""
-    sample = crop_pairs(pairs[:cores], target_s / 10e-6)
+def cpu_python_step(pairs, cores, target_s):
+    """One CPU step: the first `cores` pairs of the workload, one per host core, whole when a
+    ~10 us/cell aligner finishes them in target_s, else cropped to that budget."""
+    sample, whole = crop_pairs(pairs[:cores], target_s / 10e-6)
     t0 = time.perf_counter()
     with mp.get_context('fork').Pool(cores) as pool:
-        res = pool.map(_py_port_one, sample, chunksize=1)
+        res = pool.map(_cpu_one, sample, chunksize=1)
     wall = time.perf_counter() - t0
     cells = sum(c for c, _ in res)
-    return cells, wall, sample
+    return cells, wall, sample, whole
 
 
 def cpu_c_oracle(packed, cores, max_pairs):
@@ -225,34 +266,43 @@ def cpu_c_oracle(packed, cores, max_pairs):
     return cells, wall, k
 
 
+def sample_text(sample, whole, which, kind_text):
+    return ('%d %s of %s (seeds from the head of the workload; ~%dx%d chars each), one per host core per step; %s'
+            % (len(sample), 'whole pairs' if whole else 'cropped pairs (first rows/columns)', which,
+               len(sample[0][0]), len(sample[0][1]), kind_text))
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
     cores = len(os.sched_getaffinity(0))
-    wl = WORKLOADS[args.workload]
+    _, kind, kind_text = cpu_aligner()
     _, pairs = make_workload(args.workload, 0, cores, min(cores, 16))
     total = args.steps + args.warmup
-    target_s = max(0.5, min(20.0, 150.0 / max(total, 1)))
+    # whole run within a few minutes: ~240 s of CPU steps, a c2 page is ~21 s on one core
+    target_s = max(0.5, min(30.0, 240.0 / max(total, 1)))
     for _ in range(args.warmup):
-        cpu_python_port(pairs, cores, target_s)
+        cpu_python_step(pairs, cores, target_s)
     cells = 0
     wall = 0.0
-    sample = None
+    sample, whole = None, True
     for _ in range(args.steps):
-        c, w, sample = cpu_python_port(pairs, cores, target_s)
+        c, w, sample, whole = cpu_python_step(pairs, cores, target_s)
         cells += c
         wall += w
     gcups = cells / wall / 1e9
-    desc = ('%d crops of %s pages per step (first ~%dx%d chars of seeds 2000000..), one per host core, '
-            'pure-Python restatement of textSeqCompare.py (oracle/py_port.py); the reference is Python and '
-            'cannot travel to the GPU box' % (len(sample), args.workload, len(sample[0][0]), len(sample[0][1])))
+    per_step_cells = cells // max(args.steps, 1)
+    cfg = base_config(args.workload, len(sample), per_step_cells, 1)
+    cfg['parallelism'] = '%d host processes, one pair each' % cores
+    cfg['l2'] = 'n/a (CPU arm)'
+    cfg['sample_of_pairs'] = WORKLOADS[args.workload]['default_pairs']
     line = dict(impl='reference', metric=METRIC, value=gcups, unit='GCUPS', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=wall / max(args.steps, 1) * 1e3,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64 (python float)', data='synthetic',
-                config=dict(workload=wl['name'], scoring=list(DEFAULT_PARAMS[:6])),
-                pages_per_s=len(sample) * args.steps / wall,
-                cpu_baseline=dict(value=gcups, unit='GCUPS', cores=cores, kind='port', sample=desc),
+                config=cfg, pages_per_s=len(sample) * args.steps / wall,
+                cpu_baseline=dict(value=gcups, unit='GCUPS', cores=cores, kind=kind,
+                                  sample=sample_text(sample, whole, args.workload, kind_text)),
                 e2e=dict(value=gcups, unit='GCUPS', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
@@ -260,6 +310,292 @@ def run_reference(args):
 
 
 # ---- our arm ---------------------------------------------------------------------------------
+
+class Harness(object):
+    """Per-process state shared by the legs: torch, the rank's context, barriers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local_rank)
+        self.cpu_group = None
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local_rank))
+            # host-side barrier / gathers that leave every GPU idle (the sharded legs drive all
+            # devices from rank 0 while the other ranks wait here)
+            self.cpu_group = dist.new_group(backend='gloo')
+        import __graft_entry__ as entry
+        if self.rank == 0:
+            entry.build()
+        if self.world > 1:
+            dist.barrier()
+        from text_alignment_b200 import _native
+        from text_alignment_b200.textSeqCompare import get_context
+        self.native = _native
+        self.ctx = get_context(self.local_rank)
+        self.ctx.set_long_band_rows(args.band_rows)
+        self.cores = len(os.sched_getaffinity(0))
+        self.gen_procs = max(1, min(32, self.cores // max(self.world, 1)))
+        self.ext = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=torch.device('cuda', self.local_rank))
+        self.keep = []
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
+
+    def pinned_like(self, a):
+        """A page-locked copy of a numpy array (as a numpy view; the torch tensor is kept alive)."""
+        torch = self.torch
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        self.keep.append(t)
+        v = t.numpy()[:a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        return v
+
+    def pinned_empty(self, count, dtype, shape=None):
+        torch = self.torch
+        nbytes = int(count) * np.dtype(dtype).itemsize
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        self.keep.append(t)
+        v = t.numpy()[:nbytes].view(dtype)
+        return v.reshape(shape) if shape else v
+
+    def max_over_ranks(self, values):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device='cuda')
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def sum_over_ranks(self, values):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device='cuda')
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+
+def parity_check(h, pairs, k):
+    """First k pairs against the C oracle (outside every timed region)."""
+    from oracle import nw_oracle
+    ctx = h.ctx
+    scoring = ctx.make_scoring(*DEFAULT_PARAMS)
+    sub = pack_pairs(pairs[:k])
+    got = ctx.align_batch(*sub, scoring)
+    sc, _ = nw_oracle.make_scoring(list(DEFAULT_PARAMS[:6]), boundary_gap=DEFAULT_PARAMS[6])
+    want = nw_oracle.align_batch_codes(*sub, sc, threads=min(h.cores, 16))
+    ok = np.array_equal(got[2], want[2]) and all(
+        np.array_equal(got[0][got[1][i]:got[1][i] + got[2][i]], want[0][want[1][i]:want[1][i] + want[2][i]])
+        for i in range(k))
+    return ok and np.array_equal(got[3].astype(np.float64), np.where(want[3] <= -1e99, h.native.NEG_INF, want[3]))
+
+
+def result_digest(out, n, m, ops_len):
+    """SHA-256 over op strings (canonical layout, only the valid bytes), lengths and scores."""
+    ops, lens, scores = out
+    P = int(n.size)
+    hsh = hashlib.sha256()
+    cap = n.astype(np.int64) + m
+    off = np.concatenate([[0], np.cumsum(cap)[:-1]]) if P else np.zeros(0, np.int64)
+    mask = np.zeros(int(cap.sum()) + 1, dtype=np.int8)
+    np.add.at(mask, off, 1)
+    np.add.at(mask, off + ops_len[:P], -1)
+    valid = np.cumsum(mask[:-1]) > 0
+    hsh.update(np.ascontiguousarray(ops[:valid.size][valid]).tobytes())
+    hsh.update(np.ascontiguousarray(lens[:P]).tobytes())
+    hsh.update(np.ascontiguousarray(scores[:P]).tobytes())
+    return hsh.hexdigest()
+
+
+def measure(h, which, npairs, steps, warmup, parity_pairs, full):
+    """All legs of one workload on this rank's GPU; returns (line-fragment dict, state for the
+    sharded legs).  `full` adds the double-buffered leg."""
+    torch = h.torch
+    ctx = h.ctx
+    packed, pairs = make_workload(which, h.rank * npairs, npairs, h.gen_procs)
+    buf, t_off, n, o_off, m = packed
+    cells = int((n.astype(np.int64) * m).sum())
+    scoring = ctx.make_scoring(*DEFAULT_PARAMS)
+
+    parity = 0
+    if which != 'c5' and parity_pairs > 0:      # c5 (8e9 cells): tests/test_gpu_parity.py::test_c5_whole_manuscript_pair
+        k = min(parity_pairs, npairs)
+        if not parity_check(h, pairs, k):
+            return None, None
+        parity = k
+
+    # ---- pinned host buffers for the end-to-end legs ------------------------------------------
+    p_buf, p_toff, p_n, p_ooff, p_m = (h.pinned_like(a) for a in (buf, t_off, n, o_off, m))
+    ops_cap = int((n.astype(np.int64) + m).sum())
+
+    def out_buffers():
+        return (h.pinned_empty(max(ops_cap, 1), np.uint8), h.pinned_empty(max(npairs, 1), np.int32),
+                h.pinned_empty(max(npairs, 1) * 3, np.int32, (max(npairs, 1), 3)))
+    out = out_buffers()
+    layout = ctx.canonical_ops_layout(n, m)     # where each pair's ops go in `out`: fixed, like the buffers
+
+    # ---- leg 1: inputs resident in HBM, K launches back to back, CUDA events on the lib stream ----
+    ctx.prepare(p_buf, p_toff, p_n, p_ooff, p_m, scoring)
+    for _ in range(warmup):
+        ctx.run()
+    ctx.sync()
+    h.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record(h.ext)
+    for _ in range(steps):
+        ctx.run()
+    e1.record(h.ext)
+    ctx.sync()
+    h.barrier()
+    w1 = time.perf_counter()
+    dev_ms = e0.elapsed_time(e1)
+    launches = steps * ctx.timing()['kernel_launches']
+
+    # ---- leg 2: end to end through the C ABI with host buffers ------------------------------------
+    for _ in range(max(warmup, 5)):      # first calls on fresh pinned buffers are erratic (20-100 ms)
+        ctx.align_batch(p_buf, p_toff, p_n, p_ooff, p_m, scoring, out=out, layout=layout)
+    h.barrier()
+    x0 = time.perf_counter()
+    step_ms = []
+    for _ in range(steps):
+        s0 = time.perf_counter()
+        ctx.align_batch(p_buf, p_toff, p_n, p_ooff, p_m, scoring, out=out, layout=layout)
+        step_ms.append(round((time.perf_counter() - s0) * 1e3, 3))
+    h.barrier()
+    x1 = time.perf_counter()
+    tm = ctx.timing()
+    e2e_ms = (x1 - x0) * 1e3
+
+    # ---- leg 3: the same end-to-end steps, double buffered over two contexts ----------------------
+    # A streaming caller overlaps step k+1's upload and step k-1's download with step k's kernel
+    # by alternating two contexts (each owns a stream, device buffers and a pointer arena).  Every
+    # step still uploads its inputs from pinned host memory and downloads its results.
+    pipe_ms, same = None, None
+    if full:
+        ctx_b = h.native.Context(h.local_rank)
+        ctx_b.set_long_band_rows(ctx_b_band_rows[0])
+        out2 = out_buffers()
+        lanes = [(ctx, out), (ctx_b, out2)]
+        ops_off = layout[0]
+
+        def pipelined(k_steps):
+            pending = []
+            for k in range(k_steps):
+                c, o = lanes[k % 2]
+                if len(pending) == 2:
+                    pc, po = pending.pop(0)
+                    pc.fetch_into(ops_off, po)
+                c.prepare(p_buf, p_toff, p_n, p_ooff, p_m, c.make_scoring(*DEFAULT_PARAMS))
+                c.run()
+                pending.append((c, o))
+            for pc, po in pending:
+                pc.fetch_into(ops_off, po)
+        pipelined(4)
+        h.barrier()
+        y0 = time.perf_counter()
+        pipelined(steps)
+        h.barrier()
+        pipe_ms = (time.perf_counter() - y0) * 1e3
+        same = bool(np.array_equal(out[0][:ops_cap], out2[0][:ops_cap]))
+        ctx_b.close()
+
+    vals = [dev_ms, e2e_ms, (w1 - w0) * 1e3] + ([pipe_ms] if full else [])
+    vals = h.max_over_ranks(vals)
+    dev_ms, e2e_ms, wall_ms = vals[:3]
+    tot_cells, tot_pairs = h.sum_over_ranks([cells, npairs])
+    gcups = tot_cells * steps / (dev_ms * 1e-3) / 1e9
+    launch_s = dev_ms * 1e-3 / steps
+    frag = dict(
+        value=gcups, ms_per_step=dev_ms / steps, pages_per_s=tot_pairs * steps / (dev_ms * 1e-3),
+        wall_ms_per_step=wall_ms / steps, gpu_launches=launches, parity_checked_pairs=parity,
+        pairs_per_gpu=npairs, cells_per_gpu=cells,
+        e2e=dict(value=tot_cells * steps / (e2e_ms * 1e-3) / 1e9, unit='GCUPS', h2d_bytes_per_step=int(tm['h2d_bytes']),
+                 d2h_bytes_per_step=int(tm['d2h_bytes']), pages_per_s=tot_pairs * steps / (e2e_ms * 1e-3),
+                 ms_per_step=e2e_ms / steps, rank0_step_ms=step_ms,
+                 chunks=tm['chunks'],
+                 breakdown_ms=dict(h2d=tm['h2d_ms'], kernel=tm['kernel_ms'], d2h=tm['d2h_ms'],
+                                   host_prepare=tm['host_prepare_ms'], host_run=tm['host_run_ms'],
+                                   host_fetch=tm['host_fetch_ms'])),
+        achieved_ops=cells * OPS_PER_CELL / launch_s, achieved_gbs=cells * PTR_BYTES_PER_CELL / launch_s / 1e9)
+    if full:
+        frag['e2e']['double_buffered'] = dict(
+            value=tot_cells * steps / (vals[3] * 1e-3) / 1e9, unit='GCUPS', ms_per_step=vals[3] / steps,
+            results_identical=same, how='two contexts alternate; each step = prepare (H2D) + run + fetch (D2H)')
+    state = dict(packed=packed, pairs=pairs, out=out, pinned=(p_buf, p_toff, p_n, p_ooff, p_m), cells=cells)
+    return frag, state
+
+
+ctx_b_band_rows = [0]
+
+
+def sharded_legs(h, args, state, npairs):
+    """The product's own multi-GPU entry, timed by rank 0 while the other ranks leave their GPUs
+    idle: align_packed(devices=range(N)) on (weak) the N ranks' batches concatenated and
+    (strong) rank 0's single batch; the host-side gather is checked bit-exact against the
+    results each rank computed on its own device."""
+    from text_alignment_b200 import textSeqCompare as tsc
+    dist = h.dist
+    buf, t_off, n, o_off, m = state['packed']
+    mine = (buf, n, m, result_digest(state['out'], n, m, state['out'][1]))
+    gathered = [None] * h.world if h.rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0, group=h.cpu_group)
+    res = None
+    if h.rank == 0:
+        devices = list(range(h.world))
+        steps = max(2, min(args.steps, 5))
+        out = {}
+        # weak: one batch of N x npairs pairs
+        bufs = [g[0] for g in gathered]
+        ns = np.concatenate([g[1] for g in gathered])
+        ms = np.concatenate([g[2] for g in gathered])
+        big = np.concatenate(bufs)
+        lens = ns.astype(np.int64) + ms
+        toff = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        big_p = h.pinned_like(big)
+        for name, (sy, to, nn, mm, digests) in dict(
+                weak=(big_p, toff, ns, ms, [g[3] for g in gathered]),
+                strong=(state['pinned'][0], t_off, n, m, [gathered[0][3]])).items():
+            oo = to + nn
+            for _ in range(2):
+                r = tsc.align_packed(sy, to, nn, oo, mm, DEFAULT_PARAMS, devices=devices)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                r = tsc.align_packed(sy, to, nn, oo, mm, DEFAULT_PARAMS, devices=devices)
+            ms_step = (time.perf_counter() - t0) * 1e3 / steps
+            # bit-exact against what each rank got on its own device
+            ok = True
+            lo = 0
+            for d, dg in enumerate(digests):
+                hi = lo + (gathered[d][1].size if name == 'weak' else nn.size)
+                cap = int((nn[lo:hi].astype(np.int64) + mm[lo:hi]).sum())
+                base = int(r[1][lo])
+                ok = ok and result_digest((r[0][base:base + cap], r[2][lo:hi], r[3][lo:hi]),
+                                          nn[lo:hi], mm[lo:hi], r[2][lo:hi]) == dg
+                lo = hi
+            c = int((nn.astype(np.int64) * mm).sum())
+            out[name] = dict(pairs=int(nn.size), cells=c, devices=len(devices), ms_per_step=ms_step,
+                             value=c / (ms_step * 1e-3) / 1e9, unit='GCUPS', pages_per_s=nn.size / (ms_step * 1e-3),
+                             identical_to_single_device=bool(ok))
+        out['how'] = ('rank 0 calls textSeqCompare.align_packed(devices=range(N)) (one host thread + context per '
+                      'device, cell-balanced contiguous shards, host-side gather), wall clock of the whole call with '
+                      'host buffers, the other ranks idle on a gloo barrier; strong = one %d-pair batch over N GPUs'
+                      % npairs)
+        res = out
+    h.cpu_barrier()
+    return res
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -271,6 +607,8 @@ def main():
     ap.add_argument('--out', default='', help='also write the JSON line to this file')
     ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU per step (default: the config size)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-others', action='store_true', help='skip the short legs over the other BASELINE configs')
+    ap.add_argument('--no-sharded', action='store_true', help='skip the in-process multi-GPU legs (N > 1)')
     ap.add_argument('--parity-pairs', type=int, default=16)
     ap.add_argument('--band-rows', type=int, default=0,
                     help='cut chained-stripe pairs (c5, c1) into row bands of this height (checkpoint + recompute)')
@@ -279,210 +617,104 @@ def main():
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    ctx_b_band_rows[0] = args.band_rows
 
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
-    import __graft_entry__ as entry
-    if rank == 0:
-        entry.build()
-    if world > 1:
-        dist.barrier()
-    from text_alignment_b200 import _native
-    from text_alignment_b200.textSeqCompare import get_context
-
+    h = Harness(args)
+    ctx = h.ctx
+    rank, world = h.rank, h.world
     wl = WORKLOADS[args.workload]
     npairs = args.pairs or wl['default_pairs']
-    cores = len(os.sched_getaffinity(0))
-    gen_procs = max(1, min(32, cores // max(world, 1)))
-    packed, pairs = make_workload(args.workload, rank * npairs, npairs, gen_procs)
-    buf, t_off, n, o_off, m = packed
-    cells = int((n.astype(np.int64) * m).sum())
 
-    ctx = get_context(local_rank)
-    ctx.set_long_band_rows(args.band_rows)
-    scoring = ctx.make_scoring(*DEFAULT_PARAMS)
-
-    # ---- parity spot check against the oracle (outside every timed region) ----------------------
-    parity = 0
-    if args.workload == 'c5':
-        args.parity_pairs = 0      # 8e9 cells: checked by tests/test_gpu_parity.py::test_c5_whole_manuscript_pair
-    if args.parity_pairs > 0:
-        from oracle import nw_oracle
-        k = min(args.parity_pairs, npairs)
-        sub = pack_pairs(pairs[:k])
-        got = ctx.align_batch(*sub, scoring)
-        sc, _ = nw_oracle.make_scoring(list(DEFAULT_PARAMS[:6]), boundary_gap=DEFAULT_PARAMS[6])
-        want = nw_oracle.align_batch_codes(*sub, sc, threads=min(cores, 16))
-        ok = np.array_equal(got[2], want[2]) and all(
-            np.array_equal(got[0][got[1][i]:got[1][i] + got[2][i]], want[0][want[1][i]:want[1][i] + want[2][i]])
-            for i in range(k))
-        ok = ok and np.array_equal(got[3].astype(np.float64), np.where(want[3] <= -1e99, _native.NEG_INF, want[3]))
-        if not ok:
-            print(json.dumps(dict(error='parity check against the oracle FAILED; no number reported')))
-            return 2
-        parity = k
-
-    # ---- pinned host buffers for the end-to-end leg ------------------------------------------------
-    def pinned(a):
-        t = torch.empty(max(a.size, 1), dtype=torch.uint8, pin_memory=True)
-        v = t.numpy()[:a.size]
-        v[...] = a
-        return t, v
-    keep = []
-    p_buf = pinned(buf); keep.append(p_buf)
-    ops_cap = int((n.astype(np.int64) + m).sum())
-    t_ops = torch.empty(max(ops_cap, 1), dtype=torch.uint8, pin_memory=True)
-    t_len = torch.empty(max(npairs, 1), dtype=torch.int32, pin_memory=True)
-    t_sc = torch.empty((max(npairs, 1), 3), dtype=torch.int32, pin_memory=True)
-    out = (t_ops.numpy(), t_len.numpy(), t_sc.numpy())
-
-    ext = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device('cuda', local_rank))
     # measured issue rates (warp-lane instructions/s): IADD3, VIMNMX, fused VIADDMNMX
     # and VIADD + LOP3 together (both integer pipes busy: the issue ceiling of a kernel that mixes them)
     rate_add, rate_max, rate_fused, rate_two = (ctx.measure_int32_peak(w) for w in (0, 1, 2, 3))
     alu_pipe_peak = max(rate_add, rate_max)
     int32_peak = max(rate_two, alu_pipe_peak)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- leg 1: inputs resident in HBM, K launches back to back, CUDA events on the lib stream ----
-    ctx.prepare(p_buf[1], t_off, n, o_off, m, scoring)
-    for _ in range(args.warmup):
-        ctx.run()
-    ctx.sync()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(h.local_rank)
     sampler.start()
     time.sleep(0.3)
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
-    e0.record(ext)
-    for _ in range(args.steps):
-        ctx.run()
-    e1.record(ext)
-    ctx.sync()
-    barrier()
-    w1 = time.perf_counter()
-    dev_ms = e0.elapsed_time(e1)
-    launches = args.steps * ctx.timing()['kernel_launches']
-
-    # ---- leg 2: end to end through the C ABI with host buffers ------------------------------------
-    for _ in range(max(args.warmup, 5)):      # first calls on fresh pinned buffers are erratic (20-100 ms)
-        ctx.align_batch(p_buf[1], t_off, n, o_off, m, scoring, out=out)
-    barrier()
-    x0 = time.perf_counter()
-    step_ms = []
-    for _ in range(args.steps):
-        s0 = time.perf_counter()
-        ctx.align_batch(p_buf[1], t_off, n, o_off, m, scoring, out=out)
-        step_ms.append(round((time.perf_counter() - s0) * 1e3, 3))
-    barrier()
-    x1 = time.perf_counter()
-    tm = ctx.timing()
-    e2e_s = x1 - x0
-
-    # ---- leg 3: the same end-to-end steps, double buffered over two contexts ----------------------
-    # A streaming caller overlaps step k+1's upload and step k-1's download with step k's kernel
-    # by alternating two contexts (each owns a stream, device buffers and a pointer arena).  Every
-    # step still uploads its inputs from pinned host memory and downloads its results.
-    ctx_b = _native.Context(local_rank)
-    ctx_b.set_long_band_rows(args.band_rows)
-    t_ops2 = torch.empty(max(ops_cap, 1), dtype=torch.uint8, pin_memory=True)
-    t_len2 = torch.empty(max(npairs, 1), dtype=torch.int32, pin_memory=True)
-    t_sc2 = torch.empty((max(npairs, 1), 3), dtype=torch.int32, pin_memory=True)
-    lanes = [(ctx, out), (ctx_b, (t_ops2.numpy(), t_len2.numpy(), t_sc2.numpy()))]
-
-    def fetch_into(c, o):
-        ops_off, total = c.canonical_ops_layout(n, m)
-        c._check(c._lib.tanw_batch_fetch(c._h, _native._ptr(o[0], _native._u8p), _native._ptr(ops_off, _native._i64p),
-                                         o[0].size, _native._ptr(o[1], _native._i32p), _native._ptr(o[2], _native._i32p)))
-
-    def pipelined(steps):
-        pending = []
-        for k in range(steps):
-            c, o = lanes[k % 2]
-            if len(pending) == 2:
-                fetch_into(*pending.pop(0))
-            c.prepare(p_buf[1], t_off, n, o_off, m, c.make_scoring(*DEFAULT_PARAMS))
-            c.run()
-            pending.append((c, o))
-        for c, o in pending:
-            fetch_into(c, o)
-    pipelined(4)
-    barrier()
-    y0 = time.perf_counter()
-    pipelined(args.steps)
-    barrier()
-    y1 = time.perf_counter()
-    pipe_s = y1 - y0
-    same = bool(np.array_equal(out[0][:ops_cap], t_ops2.numpy()[:ops_cap]))
-    ctx_b.close()
-    clocks = sampler.stop(w0, y1)
+    c0 = time.perf_counter()
+    frag, state = measure(h, args.workload, npairs, args.steps, args.warmup, args.parity_pairs, full=True)
+    c1 = time.perf_counter()
+    clocks = sampler.stop(c0, c1)
+    if frag is None:
+        print(json.dumps(dict(error='parity check against the oracle FAILED; no number reported')))
+        return 2
 
     # ---- the Python list <-> buffer shim, reported separately (it is not the path) ----
     shim = None
     if rank == 0 and args.workload in ('c2', 'c4', 'c1'):
         from text_alignment_b200 import textSeqCompare as tsc_mod
-        k = min(256, npairs)
-        lists = [(list(t), list(o)) for t, o in pairs[:k]]
-        tsc_mod.perform_alignment_batch(lists[:8], devices=[local_rank])
+        k = min(2000, npairs)
+        lists = [(list(t), list(o)) for t, o in state['pairs'][:k]]
+        tsc_mod.perform_alignment_batch(lists[:8], devices=[h.local_rank])
         s0 = time.perf_counter()
-        tsc_mod.perform_alignment_batch(lists, devices=[local_rank])
+        tsc_mod.perform_alignment_batch(lists, devices=[h.local_rank])
         s1 = time.perf_counter()
+        one = lists[0]
+        tsc_mod.perform_alignment(one[0], one[1])
+        s2 = time.perf_counter()
+        for _ in range(5):
+            tsc_mod.perform_alignment(one[0], one[1])
+        s3 = time.perf_counter()
         shim = dict(pages=k, ms_per_page=(s1 - s0) * 1e3 / k, pages_per_s=k / (s1 - s0),
+                    single_call_ms=(s3 - s2) * 1e3 / 5,
                     what='perform_alignment_batch on Python lists: interning to uint8 codes, one launch, '
-                         'op strings back to two lists per page')
+                         'op strings back to two lists per page; single_call_ms = perform_alignment on one page')
 
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_s * 1e3, w1 - w0, pipe_s * 1e3], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_s, pipe_ms = t.tolist()
-        c = torch.tensor([cells, npairs], dtype=torch.float64, device='cuda')
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        tot_cells, tot_pairs = c.tolist()
-    else:
-        e2e_ms, wall_s, tot_cells, tot_pairs = e2e_s * 1e3, w1 - w0, float(cells), float(npairs)
-        pipe_ms = pipe_s * 1e3
+    # ---- the other BASELINE configs, short legs ------------------------------------------------------
+    others = None
+    if not args.no_others:
+        others = {}
+        for which in ('c1', 'c3', 'c4', 'c5'):
+            if which == args.workload:
+                continue
+            solo = which in ('c1', 'c5')          # a single pair: one GPU by definition (replicas only)
+            if solo and rank != 0:
+                h.barrier()
+                continue
+            if solo:
+                hw, hr = h.world, h.rank
+                h.world = 1                       # no cross-rank reduction inside a rank-0-only leg
+                f, _ = measure(h, which, WORKLOADS[which]['default_pairs'], 3, 3, min(args.parity_pairs, 4), full=False)
+                h.world, h.rank = hw, hr
+                h.barrier()
+            else:
+                f, _ = measure(h, which, WORKLOADS[which]['default_pairs'], 3, 3, min(args.parity_pairs, 64), full=False)
+            if f is None:
+                print(json.dumps(dict(error='parity check against the oracle FAILED on %s; no number reported' % which)))
+                return 2
+            others[which] = dict(
+                workload=WORKLOADS[which]['name'], n_gpus=1 if solo else world, value=f['value'], unit='GCUPS',
+                ms_per_step=f['ms_per_step'], pages_per_s=f['pages_per_s'], pairs_per_gpu=f['pairs_per_gpu'],
+                cells_per_gpu=f['cells_per_gpu'], steps=3, warmup=3, gpu_launches=f['gpu_launches'],
+                e2e=dict(value=f['e2e']['value'], ms_per_step=f['e2e']['ms_per_step'],
+                         h2d_bytes_per_step=f['e2e']['h2d_bytes_per_step'],
+                         d2h_bytes_per_step=f['e2e']['d2h_bytes_per_step'], breakdown_ms=f['e2e']['breakdown_ms']),
+                roofline=dict(frac=f['achieved_ops'] / int32_peak, frac_of_alu_pipe=f['achieved_ops'] / alu_pipe_peak,
+                              hbm_frac=f['achieved_gbs'] / measured_peaks()[0]),
+                parity_checked_pairs=f['parity_checked_pairs'])
+
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = sharded_legs(h, args, state, npairs)
 
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
-        gcups = tot_cells * args.steps / (dev_ms * 1e-3) / 1e9
-        e2e_gcups = tot_cells * args.steps / (e2e_ms * 1e-3) / 1e9
-        launch_s = dev_ms * 1e-3 / args.steps                     # one launch per step on this rank
-        ach_ops = cells * OPS_PER_CELL / launch_s
-        ach_gbs = cells * PTR_BYTES_PER_CELL / launch_s / 1e9
+        traffic, traffic_note = ncu_traffic(args.workload, npairs)
+        cfg = base_config(args.workload, npairs, state['cells'], world)
+        cfg.update(band_rows=args.band_rows,
+                   l2='every step writes %d MB of traceback pointers per GPU (>> 126 MB L2)' % (state['cells'] // 2 ** 20),
+                   parity_checked_pairs=frag['parity_checked_pairs'])
         line = dict(
-            metric=METRIC, value=gcups, unit='GCUPS', n_gpus=world, steps=args.steps,
-            warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='weak',
-            vs_baseline=None, dtype='int32', data='synthetic',
-            config=dict(workload=wl['name'], pairs_per_gpu=npairs, cells_per_gpu=cells,
-                        scoring=list(DEFAULT_PARAMS[:6]), band_rows=args.band_rows, parallelism='pairs sharded, %d rank(s)' % world,
-                        l2='every step writes %d MB of traceback pointers per GPU (>> 126 MB L2)' % (cells // 2 ** 20),
-                        parity_checked_pairs=parity),
-            pages_per_s=tot_pairs * args.steps / (dev_ms * 1e-3),
-            wall_ms_per_step=wall_s * 1e3 / args.steps,
-            e2e=dict(value=e2e_gcups, unit='GCUPS', h2d_bytes_per_step=int(tm['h2d_bytes']),
-                     d2h_bytes_per_step=int(tm['d2h_bytes']), pages_per_s=tot_pairs * args.steps / (e2e_ms * 1e-3),
-                     ms_per_step=e2e_ms / args.steps, rank0_step_ms=step_ms,
-                     double_buffered=dict(value=tot_cells * args.steps / (pipe_ms * 1e-3) / 1e9, unit='GCUPS',
-                                          ms_per_step=pipe_ms / args.steps, results_identical=same,
-                                          how='two contexts alternate; each step = prepare (H2D) + run + fetch (D2H)'),
-                     breakdown_ms=dict(h2d=tm['h2d_ms'], kernel=tm['kernel_ms'], d2h=tm['d2h_ms'])),
-            gpu_launches=launches,
-            roofline=dict(bound='alu', achieved=ach_ops / 1e12, peak=int32_peak / 1e12, unit='Tlane-op/s',
-                          frac=ach_ops / int32_peak, traffic=ncu_traffic(args.workload, npairs),
+            metric=METRIC, value=frag['value'], unit='GCUPS', n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=frag['ms_per_step'], higher_is_better=True, scaling='weak',
+            vs_baseline=None, dtype='int32', data='synthetic', config=cfg,
+            pages_per_s=frag['pages_per_s'], wall_ms_per_step=frag['wall_ms_per_step'],
+            e2e=frag['e2e'], gpu_launches=frag['gpu_launches'],
+            roofline=dict(bound='alu', achieved=frag['achieved_ops'] / 1e12, peak=int32_peak / 1e12, unit='Tlane-op/s',
+                          frac=frag['achieved_ops'] / int32_peak, traffic=traffic, traffic_source=traffic_note,
                           note='achieved = %d algorithmic int32 ops/cell (SURVEY 8(d)) x cells / launch time; '
                                'peak = measured dependency-free issue rate of the alu and fma integer pipes '
                                'together (VIADD + LOP3 alternating, tanw_measure_int32_peak(3)): strip_row puts '
@@ -491,30 +723,32 @@ def main():
                                % (OPS_PER_CELL, NOMINAL_INT32_PEAK / 1e12),
                           measured_rates=dict(iadd3=rate_add / 1e12, vimnmx=rate_max / 1e12,
                                               viaddmnmx=rate_fused / 1e12, viadd_plus_lop3=rate_two / 1e12),
-                          frac_of_alu_pipe=ach_ops / alu_pipe_peak,
-                          frac_of_nominal_alu_pipe=ach_ops / NOMINAL_INT32_PEAK,
-                          hbm=dict(bound='hbm', achieved=ach_gbs, peak=hbm_peak, unit='GB/s',
-                                   frac=ach_gbs / hbm_peak, peak_source=hbm_src)),
+                          frac_of_alu_pipe=frag['achieved_ops'] / alu_pipe_peak,
+                          frac_of_nominal_alu_pipe=frag['achieved_ops'] / NOMINAL_INT32_PEAK,
+                          hbm=dict(bound='hbm', achieved=frag['achieved_gbs'], peak=hbm_peak, unit='GB/s',
+                                   frac=frag['achieved_gbs'] / hbm_peak, peak_source=hbm_src)),
             clocks=clocks)
         if shim:
             line['python_list_shim'] = shim
+        if others is not None:
+            line['others'] = others
+        if sharded is not None:
+            line['sharded'] = sharded
         if not args.no_cpu_baseline:
-            t_s = 12.0
-            c_cells, c_wall, sample = cpu_python_port(pairs, cores, t_s)
-            line['cpu_baseline'] = dict(
-                value=c_cells / c_wall / 1e9, unit='GCUPS', cores=cores, kind='port',
-                sample='%d crops (~%dx%d chars) of the same pages, one per host core, pure-Python restatement '
-                       'of textSeqCompare.py (oracle/py_port.py)' % (len(sample), len(sample[0][0]), len(sample[0][1])))
-            k_cells, k_wall, k = cpu_c_oracle(packed, cores, max(cores * 4, 64))
-            line['cpu_baseline_c'] = dict(value=k_cells / k_wall / 1e9, unit='GCUPS', cores=cores, kind='port',
-                                          sample='%d full pages, oracle/nw_oracle.c (scalar C, float64), %d threads' % (k, cores))
+            _, kind, kind_text = cpu_aligner()
+            c_cells, c_wall, sample, whole = cpu_python_step(state['pairs'], h.cores, 12.0)
+            line['cpu_baseline'] = dict(value=c_cells / c_wall / 1e9, unit='GCUPS', cores=h.cores, kind=kind,
+                                        sample=sample_text(sample, whole, args.workload, kind_text))
+            k_cells, k_wall, k = cpu_c_oracle(state['packed'], h.cores, max(h.cores * 4, 64))
+            line['cpu_baseline_c'] = dict(value=k_cells / k_wall / 1e9, unit='GCUPS', cores=h.cores, kind='port',
+                                          sample='%d full pages, oracle/nw_oracle.c (scalar C, float64), %d threads' % (k, h.cores))
         print(json.dumps(line))
         if args.out:
             with open(args.out, 'w') as f:
                 json.dump(line, f, indent=1)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        h.dist.barrier()
+        h.dist.destroy_process_group()
     return 0
 
 

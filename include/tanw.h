@@ -12,10 +12,20 @@
  *   - every function returns 0 on success, a TANW_E_* code otherwise; the message is
  *     available from tanw_last_error(ctx) (or tanw_last_error(NULL) for create failures);
  *   - the caller owns every host buffer and keeps it alive for the duration of the call;
- *     the library owns device memory, streams and staging inside the context;
+ *     the library owns device memory, streams and staging inside the context.  One exception
+ *     in the three-phase form: tanw_batch_prepare returns while `symbols` is still being copied
+ *     (that is what lets a double-buffering caller overlap it with another context's kernel), so
+ *     `symbols` must stay valid and unmodified until tanw_batch_fetch or tanw_sync has returned;
+ *     the pair arrays and the scoring system(s) are consumed before prepare returns;
  *   - a context is single-caller; distinct contexts (one per GPU) may be driven from
  *     distinct host threads concurrently (that is the multi-GPU model);
- *   - there is no CPU fallback: without an sm_100 device tanw_create fails.
+ *   - every entry runs on the context's device and restores the caller's current CUDA device
+ *     before it returns;
+ *   - there is no CPU fallback: without an sm_100 device tanw_create fails;
+ *   - scores are int32 fixed point on the device: a batch is refused with TANW_E_RANGE unless
+ *     (max(n+m) + 2) * max|parameter| < 2^22, where the parameters are match, mismatch,
+ *     gap_open+gap_extend, gap_extend (both axes), boundary_gap and every table entry -- e.g.
+ *     default_sys (max 10) allows n+m up to 419 428, a callable returning +-100 up to 41 941.
  *
  * Data model (replaces the Python lists of textSeqCompare.py:13, :21-22)
  *   symbols : uint8 codes (uint16 after tanw_set_symbol_bytes(ctx, 2)), all sequences of the
@@ -48,6 +58,7 @@ extern "C" {
 #define TANW_E_NODEVICE    4   /* no sm_100 device / device index out of range                */
 #define TANW_E_NOMEM       5   /* host or device allocation failed                            */
 #define TANW_E_STATE       6   /* call order violated (run before prepare, ...)               */
+#define TANW_E_INTERNAL    7   /* a device assertion failed (TANW_CHECKED builds only)        */
 
 #define TANW_NEG_INF       (-1073741824)   /* int32 stand-in for -1e100 in score outputs */
 
@@ -91,6 +102,8 @@ typedef struct tanw_timing {
     int64_t h2d_bytes, d2h_bytes;
     /* host wall-clock spent inside the three phases (includes the waits on the device) */
     float   host_prepare_ms, host_run_ms, host_fetch_ms;
+    int32_t chunks;           /* chunks the batch was pipelined in (1 in the three-phase form)  */
+    int32_t table_launches;   /* small kernels launched by prepare to build the batch tables    */
 } tanw_timing;
 
 /* ---- library / device queries ------------------------------------------------------------ */
@@ -119,8 +132,9 @@ int  tanw_set_long_band_rows(tanw_ctx *ctx, int rows);
 /* Width of a symbol code in bytes: 1 (default) or 2.  With 2, `symbols` in the batch calls points
  * to uint16 codes (pass the array's address), symbols_len / t_off / o_off still count symbols,
  * and subst_k may be up to 2048.  For pairs with more than 256 distinct elements (the reference
- * accepts any hashable, textSeqCompare.py:13-22).  Such batches run on the page kernel only (one
- * warp per pair); a pair whose pointers exceed one warp's share of the arena is refused. */
+ * accepts any hashable, textSeqCompare.py:13-22).  Such batches run on the page kernel (one warp
+ * per pair, general recurrences); a pair whose pointers exceed one warp's share of the arena takes
+ * the chained-stripe path and its row bands like any other. */
 int  tanw_set_symbol_bytes(tanw_ctx *ctx, int bytes);
 /* Pairs with m <= 128 and n <= 4096 are aligned four per warp by the line kernel (8 lanes per
  * pair; BASELINE config 3).  enabled = 0 sends them through the page kernel instead (same
@@ -139,17 +153,37 @@ int  tanw_align_batch(tanw_ctx *ctx,
                       uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
                       int32_t *ops_len, int32_t *scores);
 
+/* The same with a scoring system per pair: pair p is aligned under scorings[scoring_idx[p]].  This
+ * is the reference's parameter sweep (evaluate_text_alignment.py:134-194: 729 integer scoring
+ * vectors x 3 pages = 2187 independent alignments) as ONE batch: the pages' symbols are uploaded
+ * once and several pairs may name the same t_off / o_off.  Equality scorers only (subst == NULL),
+ * 8-bit symbol codes. */
+int  tanw_align_batch_multi(tanw_ctx *ctx,
+                            const uint8_t *symbols, int64_t symbols_len,
+                            const int64_t *t_off, const int32_t *n,
+                            const int64_t *o_off, const int32_t *m,
+                            int64_t n_pairs, const tanw_scoring *scorings, int32_t n_scorings,
+                            const int32_t *scoring_idx,
+                            uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
+                            int32_t *ops_len, int32_t *scores);
+
 /* ---- the same in three phases (bench.py times `run` alone with inputs resident in HBM) ------ */
 int  tanw_batch_prepare(tanw_ctx *ctx,
                         const uint8_t *symbols, int64_t symbols_len,
                         const int64_t *t_off, const int32_t *n,
                         const int64_t *o_off, const int32_t *m,
                         int64_t n_pairs, const tanw_scoring *scoring);
+int  tanw_batch_prepare_multi(tanw_ctx *ctx,
+                              const uint8_t *symbols, int64_t symbols_len,
+                              const int64_t *t_off, const int32_t *n,
+                              const int64_t *o_off, const int32_t *m,
+                              int64_t n_pairs, const tanw_scoring *scorings, int32_t n_scorings,
+                              const int32_t *scoring_idx);
 int  tanw_batch_run(tanw_ctx *ctx);                       /* asynchronous on the ctx stream     */
-/* Replace the scoring system of the prepared batch; the sequences stay resident in HBM.  This
- * is the reference's parameter sweep (evaluate_text_alignment.py:134-198: 729 integer scoring
- * vectors over the same pages): prepare once, then { rescore, run, fetch } per vector.  An
- * equality scorer may be replaced by another equality scorer, a table by a table of the same K. */
+/* Replace the scoring system of the prepared batch; the sequences stay resident in HBM: prepare
+ * once, then { rescore, run, fetch } per system (one launch each; tanw_align_batch_multi runs a
+ * whole sweep as one launch).  An equality scorer may be replaced by another equality scorer, a
+ * table by a table of the same K. */
 int  tanw_batch_rescore(tanw_ctx *ctx, const tanw_scoring *scoring);
 int  tanw_batch_fetch(tanw_ctx *ctx,
                       uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,

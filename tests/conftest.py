@@ -16,6 +16,24 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'slow: minutes-long CPU test')
 
 
+def _device_count():
+    try:
+        from text_alignment_b200 import _native
+        return _native.device_count()
+    except Exception:                    # library not built, no driver, ...
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a device: on a box without one they are skipped with a reason instead of
+    failing with NativeError (the driver's CPU run deselects them with -m "not gpu" anyway)."""
+    gpu_items = [it for it in items if it.get_closest_marker('gpu')]
+    if gpu_items and _device_count() == 0:
+        skip = pytest.mark.skip(reason='no CUDA device on this box')
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 def load_golden(name):
     with open(os.path.join(GOLDEN, name)) as f:
         return json.load(f)

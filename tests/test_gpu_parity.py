@@ -593,3 +593,130 @@ def test_small_arena_limit_reduces_occupancy_not_correctness(oracle):
         _check_ctx_vs_oracle(ctx, oracle, pairs[:3])
     finally:
         ctx.close()
+
+
+# ---- round 2: one-launch sweep, batch-wide tables, pipelined batches, shared contexts ------------
+
+def test_parameter_sweep_is_one_launch(tsc, oracle):
+    """evaluate_text_alignment.py:134-194: 729 scoring vectors x 3 pages = 2187 independent
+    alignments; here all of them are ONE batch with per-pair scoring systems
+    (tanw_align_batch_multi), including vectors that need the general recurrences."""
+    from itertools import product
+    grid = [list(p) for p in product([5, 8, 11], [-4, -7, -10], [-2, -5, -7], [-2, -5, -7], [0, -3, -5], [0, -3, -5])]
+    pages = [(list(t), list(o)) for t, o in (synth.make_pair(700 + k, 260 + 40 * k, 330 + 50 * k, 3, 25) for k in range(3))]
+    got = tsc.perform_alignment_sweep(pages, grid, return_scores=True)
+    tm = tsc.get_context(0).timing()
+    assert tm['kernel_launches'] == 1 and tm['cells'] == 729 * sum(len(t) * len(o) for t, o in pages)
+    rng = random.Random(11)
+    for k in rng.sample(range(729), 40) + [0, 728]:
+        for (T, O), (tra, ocr, score) in zip(pages, got[k]):
+            want = oracle.perform_alignment(T, O, grid[k], full=True)
+            assert (tra, ocr) == (want[0], want[1]), grid[k]
+            assert tuple(score) == _end(want[2]['end'])
+    # mixed variants in one batch: a positive gap open forces the general recurrences for all
+    mixed = [[8, -4, -7, -7, -3, 0], [7, 2, 3, -4, -1, 1], [5, -4, -2, -7, 0, -5], [10, -5, -7, -7]]
+    got = tsc.perform_alignment_sweep(pages + [(list('dominus'), list('dns')), ([], list('ab'))], mixed, return_scores=True)
+    for system, res in zip(mixed, got):
+        for (T, O), (tra, ocr, score) in zip(pages + [(list('dominus'), list('dns')), ([], list('ab'))], res):
+            want = oracle.perform_alignment(T, O, system, full=True)
+            assert (tra, ocr) == (want[0], want[1]) and tuple(score) == _end(want[2]['end']), system
+
+
+def test_callable_scorer_batch_shares_one_table(tsc, oracle):
+    """A callable scorer (textSeqCompare.py:27-29) over a batch: the batch is interned once, one
+    K x K table serves every pair and the whole batch is one launch per kernel family."""
+    def fn(a, b):
+        return 6 if a == b else (-1 if (a in 'aeiou') == (b in 'aeiou') else -5)
+    pairs = [(list(t), list(o)) for t, o in
+             [synth.c3_pair(k) for k in range(150)] + [synth.make_pair(50 + k, 300, 420, 3, 30) for k in range(6)]]
+    pairs += [([], list('ab')), (list('dominus'), list('dns'))]
+    for system in ([fn, -7, -6, -3, -1], [fn, -7, -7, -3, 0], [fn, 2, -6, -3, -1]):
+        got = tsc.perform_alignment_batch(pairs, system, return_scores=True)
+        assert tsc.get_context(0).timing()['kernel_launches'] <= 2          # line kernel + page kernel
+        for (T, O), (tra, ocr, score) in zip(pairs, got):
+            want = oracle.perform_alignment(T, O, system, full=True)
+            assert (tra, ocr) == (want[0], want[1]), system[1:]
+            assert tuple(score) == _end(want[2]['end'])
+
+
+def test_pipelined_batch_equals_three_phase(tsc, oracle):
+    """tanw_align_batch cuts a copy-heavy batch into chunks (uploads, kernels and downloads
+    overlap); the three-phase form runs the same batch as one chunk.  Same bytes either way."""
+    from text_alignment_b200 import _native
+    pairs = [synth.c3_pair(k) for k in range(70000)]
+    pairs[12345] = ('', 'abc')
+    pairs[40000] = synth.make_pair(5, 150, 210, 5, 40)         # a small page among the lines
+    buf, t_off, n, o_off, m = _pack(pairs)
+    ctx = _native.Context(0)
+    try:
+        sc = ctx.make_scoring(*DEFAULT)
+        one = ctx.align_batch(buf, t_off, n, o_off, m, sc)
+        assert ctx.timing()['chunks'] > 1
+        ctx.prepare(buf, t_off, n, o_off, m, sc)
+        ctx.run()
+        three = ctx.fetch()
+        assert ctx.timing()['chunks'] == 1
+        assert np.array_equal(one[2], three[2]) and np.array_equal(one[3], three[3])
+        valid = np.zeros(one[0].size + 1, dtype=np.int32)
+        np.add.at(valid, one[1], 1)
+        np.add.at(valid, one[1] + one[2], -1)
+        mask = np.cumsum(valid[:-1]) > 0
+        assert np.array_equal(one[0][mask], three[0][:mask.size][mask])
+    finally:
+        ctx.close()
+    sample = list(range(0, 70000, 997)) + [12345, 40000]
+    osc, _ = oracle.make_scoring(list(DEFAULT[:6]), boundary_gap=DEFAULT[6])
+    sub = _pack([pairs[k] for k in sample])
+    r_ops, r_off, r_len, r_end = oracle.align_batch_codes(*sub, osc, threads=8)
+    for j, k in enumerate(sample):
+        assert np.array_equal(one[0][one[1][k]:one[1][k] + one[2][k]], r_ops[r_off[j]:r_off[j] + r_len[j]]), k
+        assert tuple(None if v == -1073741824 else int(v) for v in one[3][k].tolist()) == _end(r_end[j].tolist())
+
+
+def test_two_threads_share_one_context(tsc, oracle):
+    """The reference function is pure and re-entrant; here two Python threads calling the
+    drop-in at once share the device's context and are serialised by its lock."""
+    import threading
+    jobs = [(list(t), list(o)) for t, o in (synth.make_pair(300 + k, 120 + 7 * k, 150 + 5 * k, 2, 12) for k in range(24))]
+    want = [oracle.perform_alignment(T, O, None) for T, O in jobs]
+    results = {}
+    errors = []
+
+    def work(tid):
+        try:
+            for rep in range(6):
+                for k in range(tid, len(jobs), 2):
+                    results[(tid, rep, k)] = tsc.perform_alignment(jobs[k][0], jobs[k][1])
+        except BaseException as e:       # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors
+    assert len(results) == 6 * len(jobs)
+    for (tid, rep, k), got in results.items():
+        assert (got[0], got[1]) == (want[k][0], want[k][1])
+
+
+def test_wide_symbol_pair_beyond_the_arena_is_banded(oracle):
+    """16-bit symbol codes on the chained-stripe path: a pair whose pointers exceed one warp's
+    share of the arena is cut into row bands like any other (round 1 refused it)."""
+    from text_alignment_b200 import _native
+    t, o = synth.make_pair(9, 700, 900, 3, 30)
+    buf, t_off, n, o_off, m = _pack([(t, o), ('abc', 'abd')])
+    ctx = _native.Context(0)
+    try:
+        narrow = ctx.align_batch(buf, t_off, n, o_off, m, ctx.make_scoring(*DEFAULT))
+        ctx.set_arena_limit(512 << 10)
+        for params in (DEFAULT, (7, 2, -4, 3, -1, 1, 0)):
+            narrow = ctx.align_batch(buf, t_off, n, o_off, m, ctx.make_scoring(*params))
+            wide = ctx.align_batch(buf.astype(np.uint16), t_off, n, o_off, m, ctx.make_scoring(*params))
+            assert np.array_equal(narrow[2], wide[2]) and np.array_equal(narrow[3], wide[3])
+            for k in range(2):
+                assert np.array_equal(narrow[0][narrow[1][k]:narrow[1][k] + narrow[2][k]],
+                                      wide[0][wide[1][k]:wide[1][k] + wide[2][k]])
+    finally:
+        ctx.close()
+    _ = oracle

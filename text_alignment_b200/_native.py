@@ -7,7 +7,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get('TANW_LIB') or os.path.join(_HERE, 'libtanw.so')   # TANW_LIB: kernel-variant experiments
+LIB_PATH = os.path.join(_HERE, 'libtanw.so')
 
 NEG_INF = -1073741824          # TANW_NEG_INF
 
@@ -35,7 +35,7 @@ class Timing(ctypes.Structure):
                 ('kernel_launches', ctypes.c_int32), ('cells', ctypes.c_int64), ('ptr_bytes', ctypes.c_int64),
                 ('h2d_bytes', ctypes.c_int64), ('d2h_bytes', ctypes.c_int64),
                 ('host_prepare_ms', ctypes.c_float), ('host_run_ms', ctypes.c_float),
-                ('host_fetch_ms', ctypes.c_float)]
+                ('host_fetch_ms', ctypes.c_float), ('chunks', ctypes.c_int32), ('table_launches', ctypes.c_int32)]
 
 
 # every symbol include/tanw.h declares: (restype, argtypes)
@@ -54,6 +54,11 @@ SIGNATURES = {
     'tanw_set_line_kernel': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_align_batch': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                         ctypes.POINTER(Scoring), _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
+    'tanw_align_batch_multi': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
+                                              ctypes.POINTER(Scoring), ctypes.c_int32, _i32p,
+                                              _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
+    'tanw_batch_prepare_multi': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
+                                                ctypes.POINTER(Scoring), ctypes.c_int32, _i32p]),
     'tanw_batch_prepare': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                           ctypes.POINTER(Scoring)]),
     'tanw_batch_run': (ctypes.c_int, [_VOIDP]),
@@ -94,6 +99,28 @@ def _ptr(a, ct):
     return a.ctypes.data_as(ct)
 
 
+_pylist = None
+
+
+def pylist():
+    """The CPython-side list marshalling helper (csrc/tanw_pylist.c), or None when it was not
+    built: it only speeds up list <-> code conversion, the numpy path gives the same results."""
+    global _pylist
+    if _pylist is None:
+        path = os.path.join(_HERE, '_tanw_pylist.so')
+        try:
+            lib = ctypes.PyDLL(path)
+            lib.tanw_pylist_codepoints.restype = ctypes.c_ssize_t
+            lib.tanw_pylist_codepoints.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_void_p]
+            lib.tanw_pylist_expand.restype = ctypes.py_object
+            lib.tanw_pylist_expand.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_int,
+                                               ctypes.py_object]
+            _pylist = lib
+        except (OSError, AttributeError):
+            _pylist = False
+    return _pylist or None
+
+
 def device_count():
     c = ctypes.c_int(0)
     rc = load().tanw_device_count(ctypes.byref(c))
@@ -113,10 +140,14 @@ def device_info(device=0):
 
 
 class Context(object):
-    """One per GPU.  Single-caller; distinct contexts may run on distinct threads (ctypes
-    releases the GIL for the duration of each native call)."""
+    """One per GPU.  The native context is single-caller (include/tanw.h), and ctypes releases
+    the GIL for the duration of each native call, so every entry that touches the batch state
+    holds ``self.lock`` (re-entrant): two Python threads may share a Context and are serialised,
+    distinct contexts run concurrently.  Callers of the three-phase form (prepare / rescore / run
+    / fetch) that share a Context between threads hold ``ctx.lock`` across the whole sequence."""
 
     def __init__(self, device=0):
+        self.lock = threading.RLock()
         self._lib = load()
         h = _VOIDP()
         rc = self._lib.tanw_create(int(device), ctypes.byref(h))
@@ -147,6 +178,8 @@ class Context(object):
                 raise ValueError(msg)
             if rc == 5:
                 raise MemoryError(msg)
+            if rc == 7:
+                raise AssertionError(msg)
             raise NativeError('libtanw error %d: %s' % (rc, msg))
 
     def set_arena_limit(self, nbytes):
@@ -209,14 +242,16 @@ class Context(object):
             np.cumsum(cap[:-1], out=off[1:])
         return off, int(cap.sum())
 
-    def align_batch(self, symbols, t_off, n, o_off, m, scoring, want_scores=True, out=None):
+    def align_batch(self, symbols, t_off, n, o_off, m, scoring, want_scores=True, out=None, layout=None):
         """One call = H2D + fill + traceback + D2H.  Returns (ops, ops_off, ops_len, scores).
-        `out` = (ops, ops_len, scores) preallocated arrays (e.g. pinned) to receive the results."""
+        `out` = (ops, ops_len, scores) preallocated arrays (e.g. pinned) to receive the results;
+        `layout` = canonical_ops_layout(n, m) computed earlier by a caller that reuses its output
+        buffers (the prefix sums are host work of the same order as the call itself for 10^5
+        short pairs)."""
         symbols, t_off, n, o_off, m = self._canon(symbols, t_off, n, o_off, m)
-        self._symbol_width(symbols)
         sc, keep = scoring
         P = int(n.size)
-        ops_off, total = self.canonical_ops_layout(n, m)
+        ops_off, total = layout if layout is not None else self.canonical_ops_layout(n, m)
         if out is not None:
             ops, ops_len, scores = out
             if ops.size < total or ops_len.size < P or (want_scores and scores.size < 3 * P):
@@ -225,34 +260,69 @@ class Context(object):
             ops = np.empty(max(total, 1), dtype=np.uint8)
             ops_len = np.zeros(max(P, 1), dtype=np.int32)
             scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
-        rc = self._lib.tanw_align_batch(self._h, symbols.ctypes.data_as(_u8p), symbols.size, _ptr(t_off, _i64p), _ptr(n, _i32p),
-                                        _ptr(o_off, _i64p), _ptr(m, _i32p), P, ctypes.byref(sc),
-                                        _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size, _ptr(ops_len, _i32p),
-                                        _ptr(scores, _i32p) if want_scores else None)
-        self._check(rc)
+        with self.lock:
+            self._symbol_width(symbols)
+            rc = self._lib.tanw_align_batch(self._h, symbols.ctypes.data_as(_u8p), symbols.size, _ptr(t_off, _i64p),
+                                            _ptr(n, _i32p), _ptr(o_off, _i64p), _ptr(m, _i32p), P, ctypes.byref(sc),
+                                            _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size, _ptr(ops_len, _i32p),
+                                            _ptr(scores, _i32p) if want_scores else None)
+            self._check(rc)
+        return ops, ops_off, ops_len[:P], (scores[:P] if want_scores else None)
+
+    def align_batch_multi(self, symbols, t_off, n, o_off, m, scorings, scoring_idx, want_scores=True):
+        """Every pair under its own scoring system (the reference's parameter sweep as one launch):
+        ``scorings`` = list of (match, mismatch, gox, goy, gex, gey, boundary_gap) tuples,
+        ``scoring_idx[p]`` = which of them pair p uses.  Returns (ops, ops_off, ops_len, scores)."""
+        symbols, t_off, n, o_off, m = self._canon(symbols, t_off, n, o_off, m)
+        if symbols.dtype != np.uint8:
+            raise ValueError('per-pair scoring systems need 8-bit symbol codes')
+        sidx = np.ascontiguousarray(scoring_idx, dtype=np.int32)
+        if sidx.size != n.size:
+            raise ValueError('scoring_idx and the pair table differ in length')
+        arr = (Scoring * max(len(scorings), 1))()
+        for k, prm in enumerate(scorings):
+            sc, _ = self.make_scoring(*prm)
+            arr[k] = sc
+        P = int(n.size)
+        ops_off, total = self.canonical_ops_layout(n, m)
+        ops = np.empty(max(total, 1), dtype=np.uint8)
+        ops_len = np.zeros(max(P, 1), dtype=np.int32)
+        scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
+        with self.lock:
+            self._symbol_width(symbols)
+            rc = self._lib.tanw_align_batch_multi(self._h, symbols.ctypes.data_as(_u8p), symbols.size, _ptr(t_off, _i64p),
+                                                  _ptr(n, _i32p), _ptr(o_off, _i64p), _ptr(m, _i32p), P, arr,
+                                                  len(scorings), _ptr(sidx, _i32p), _ptr(ops, _u8p),
+                                                  _ptr(ops_off, _i64p), ops.size, _ptr(ops_len, _i32p),
+                                                  _ptr(scores, _i32p) if want_scores else None)
+            self._check(rc)
         return ops, ops_off, ops_len[:P], (scores[:P] if want_scores else None)
 
     # ---- three-phase form (bench.py times run() alone with the inputs resident in HBM) ----
     def prepare(self, symbols, t_off, n, o_off, m, scoring):
         symbols, t_off, n, o_off, m = self._canon(symbols, t_off, n, o_off, m)
-        self._symbol_width(symbols)
         sc, keep = scoring
-        self._keep = (symbols, t_off, n, o_off, m, sc, keep)
-        self._check(self._lib.tanw_batch_prepare(self._h, symbols.ctypes.data_as(_u8p), symbols.size, _ptr(t_off, _i64p),
-                                                 _ptr(n, _i32p), _ptr(o_off, _i64p), _ptr(m, _i32p), int(n.size),
-                                                 ctypes.byref(sc)))
+        with self.lock:
+            self._symbol_width(symbols)
+            self._keep = (symbols, t_off, n, o_off, m, sc, keep)
+            self._check(self._lib.tanw_batch_prepare(self._h, symbols.ctypes.data_as(_u8p), symbols.size,
+                                                     _ptr(t_off, _i64p), _ptr(n, _i32p), _ptr(o_off, _i64p),
+                                                     _ptr(m, _i32p), int(n.size), ctypes.byref(sc)))
 
     def rescore(self, scoring):
         """New scoring system for the prepared batch (sequences stay resident in HBM)."""
         sc, keep = scoring
-        self._keep = self._keep[:5] + (sc, keep)
-        self._check(self._lib.tanw_batch_rescore(self._h, ctypes.byref(sc)))
+        with self.lock:
+            self._keep = self._keep[:5] + (sc, keep)
+            self._check(self._lib.tanw_batch_rescore(self._h, ctypes.byref(sc)))
 
     def run(self):
-        self._check(self._lib.tanw_batch_run(self._h))
+        with self.lock:
+            self._check(self._lib.tanw_batch_run(self._h))
 
     def sync(self):
-        self._check(self._lib.tanw_sync(self._h))
+        with self.lock:
+            self._check(self._lib.tanw_sync(self._h))
 
     def fetch(self, want_scores=True):
         _, _, n, _, m, _, _ = self._keep
@@ -261,9 +331,17 @@ class Context(object):
         ops = np.empty(max(total, 1), dtype=np.uint8)
         ops_len = np.zeros(max(P, 1), dtype=np.int32)
         scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
-        self._check(self._lib.tanw_batch_fetch(self._h, _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size,
-                                               _ptr(ops_len, _i32p), _ptr(scores, _i32p) if want_scores else None))
+        self.fetch_into(ops_off, (ops, ops_len, scores))
         return ops, ops_off, ops_len[:P], (scores[:P] if want_scores else None)
+
+    def fetch_into(self, ops_off, out):
+        """Results of the batch that ran into caller-owned (e.g. pinned) arrays
+        ``out = (ops, ops_len, scores or None)``; ``ops_off`` as from canonical_ops_layout."""
+        ops, ops_len, scores = out
+        with self.lock:
+            self._check(self._lib.tanw_batch_fetch(self._h, _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size,
+                                                   _ptr(ops_len, _i32p),
+                                                   _ptr(scores, _i32p) if scores is not None else None))
 
     def timing(self):
         t = Timing()

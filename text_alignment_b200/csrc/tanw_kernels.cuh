@@ -76,7 +76,19 @@ struct BatchArgs {
     uint8_t        *ops;         // out
     int            *ops_len;     // out
     int            *scores;      // out, 3 per pair (may be null)
+    const KParams  *kparams;     // MULTI kernels: the scoring systems of the batch ...
+    const int      *sidx;        // ... and which of them pair p uses (evaluate_text_alignment.py:181-194)
+    int            *check;       // TANW_CHECKED builds: first failed device assertion (0 = none)
 };
+
+// Device assertions of the TANW_CHECKED build (tools/stress_gpu.py runs under it): the first failure
+// leaves its code in BatchArgs::check / LongArgs::check and the host turns it into an error.  The
+// shipping build compiles them out.
+#ifdef TANW_CHECKED
+#define TANW_ASSERT(word, cond, code) do { if ((word) && !(cond)) atomicCAS((word), 0, (code)); } while (0)
+#else
+#define TANW_ASSERT(word, cond, code) do { } while (0)
+#endif
 
 // Width of the remainder pass: smallest multiple of 4 columns per lane covering r columns.
 __host__ __device__ inline int remainder_c(int r) { return ((r + 127) / 128) * 4; }
@@ -104,6 +116,14 @@ __device__ __forceinline__ int clean_tag_or(int v, int tag)
     int r;
     asm("lop3.b32 %0, %1, 0xFFFFFFFC, %2, 0xEA;" : "=r"(r) : "r"(v), "r"(tag));   // (v & ~3) | tag
     return r;
+}
+
+// Symbol codes index the K x K table of a tabulated scorer: a code >= K (which the host reports as
+// an error after the batch) must not read outside the table.
+template <bool SUBST>
+__device__ __forceinline__ int table_code(int v, const KParams &kp)
+{
+    return SUBST ? min(v, kp.subst_k - 1) : v;
 }
 
 // Kernel variants (template parameter VAR):
@@ -147,7 +167,7 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
         const int dc = clean_tag(dul);
         int m2;
         if (SUBST) {
-            m2 = dc + __ldg(srow + s.oc[k]);
+            m2 = dc + srow[s.oc[k]];            // generic load: the table is in shared memory when K <= kSubstSmemK
         } else {
             // compare + add + predicated add instead of compare + select + add: ptxas turns the
             // two adds into VIADD, which B200 issues on whichever of the alu / fma pipes is free
@@ -250,12 +270,13 @@ struct Chain {
     int *ck_out;           // where to leave the state of the band's last row, or null
     int m;                 // columns = stride of the checkpoint arrays
     bool store;            // write pointer bytes (false in the forward checkpointing sweep)
+    int *check;            // TANW_CHECKED builds: first failed device assertion
 };
 __device__ __forceinline__ Chain no_chain()
 {
     Chain c;
     c.in = nullptr; c.out = nullptr; c.epoch = 0;
-    c.r0 = 0; c.ck_in = nullptr; c.ck_out = nullptr; c.m = 0; c.store = true;
+    c.r0 = 0; c.ck_in = nullptr; c.ck_out = nullptr; c.m = 0; c.store = true; c.check = nullptr;
     return c;
 }
 constexpr int kChainBlock = 8;         // boundary rows fetched per coalesced load (lanes 0..7)
@@ -285,9 +306,18 @@ __device__ __forceinline__ int4 chain_issue(const Chain &ch, int base, int n, in
 __device__ __forceinline__ int2 chain_take(const Chain &ch, int4 v, int base, int n, int lane)
 {
     const bool mine = lane < kChainBlock && base + lane <= n;
+#ifdef TANW_CHECKED
+    const long long t0 = clock64();
+#endif
     while (!__all_sync(kFull, v.y == ch.epoch && v.w == ch.epoch)) {
         if (mine) v = ld_volatile_v4(ch.in + base + lane);
+#ifdef TANW_CHECKED
+        // a record is either untouched by this launch (both stamps stale) or complete, or torn for
+        // an instant; a stripe that waits for seconds has lost its producer
+        if (clock64() - t0 > (1ll << 33)) { TANW_ASSERT(ch.check, false, 3); break; }
+#endif
     }
+    TANW_ASSERT(ch.check, !mine || (v.y == ch.epoch && v.w == ch.epoch), 4);
     return make_int2(v.x, v.z);
 }
 
@@ -327,10 +357,10 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
         // a stripe has its scheduler to itself: one step does not cover the load latency
         ps.tnext = ps.tnext2;
         if (!GUARDED || (i + 1 >= 0 && i + 1 < n))
-            ps.tnext2 = (int)__ldg(reinterpret_cast<const SYM *>(ps.tp) + 1);           // row i+2 reads T[i+1]
+            ps.tnext2 = table_code<SUBST>((int)__ldg(reinterpret_cast<const SYM *>(ps.tp) + 1), kp);   // row i+2 reads T[i+1]
     } else {
         if (!GUARDED || (i >= 0 && i < n))
-            ps.tnext = (int)__ldg(reinterpret_cast<const SYM *>(ps.tp));     // row i+1 reads T[i]
+            ps.tnext = table_code<SUBST>((int)__ldg(reinterpret_cast<const SYM *>(ps.tp)), kp);     // row i+1 reads T[i]
     }
     if (!GUARDED || (i >= 1 && i <= n)) {
         unsigned pw[C / 4];
@@ -391,7 +421,7 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restri
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         const int c = c0 + k;
-        s.oc[k] = (c < m) ? (int)__ldg(O + c) : (1 << (8 * sizeof(SYM)));   // never equals a symbol
+        s.oc[k] = (c < m) ? table_code<SUBST>((int)__ldg(O + c), kp) : (1 << (8 * sizeof(SYM)));   // never equals a symbol
         if (SUBST && c >= m) s.oc[k] = 0;
         // row 0: M[0][j] = X[0][j] = bg*j, Y[0][j] = -inf   (textSeqCompare.py:57-60)
         const int base = kp.bg * (c + 1);
@@ -426,11 +456,11 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restri
     }
     ps.bp = bnd + 2;
     ps.bw = bnd_out + (1 - lane);
-    ps.tnext = (lane == 0) ? (int)__ldg(T) : 0;
+    ps.tnext = (lane == 0) ? table_code<SUBST>((int)__ldg(T), kp) : 0;
     ps.tnext2 = 0;
     if (CHAINED) {
-        if (lane == 0 && n > 1) ps.tnext2 = (int)__ldg(T + 1);
-        if (lane == 1) ps.tnext2 = (int)__ldg(T);
+        if (lane == 0 && n > 1) ps.tnext2 = table_code<SUBST>((int)__ldg(T + 1), kp);
+        if (lane == 1) ps.tnext2 = table_code<SUBST>((int)__ldg(T), kp);
     }
     ps.tp = reinterpret_cast<const uint8_t *>(T + (1 - lane));
     ps.xe = kp.ex * (1 - lane);                   // row i = t - lane at t = 1
@@ -700,6 +730,7 @@ __device__ __forceinline__ int traceback_warp(const uint8_t *ptr, int n, int m, 
         while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // OCR remainder first       (:154-158)
         while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // then transcript remainder (:160-164)
     }
+    __syncwarp();                       // lane 0's op bytes are read by every lane next
     return __shfl_sync(kFull, k, 0);
 }
 
@@ -711,18 +742,40 @@ __device__ __forceinline__ int score_out(int v)
 #ifndef TANW_MINB
 #define TANW_MINB 4
 #endif
+constexpr int kSubstSmemK = 64;      // substitution tables up to this side are staged in shared memory (16 KB)
+
+// A tabulated scorer's K x K table (textSeqCompare.py:27-29), staged in shared memory when it
+// fits: every cell reads one entry, and the whole block shares the table.  Returns the KParams the
+// block uses from here on (subst points at the staged copy).  All threads of the block call it.
+__device__ __forceinline__ KParams stage_subst(const KParams &kp, int *stab)
+{
+    KParams out = kp;
+    if (kp.subst != nullptr && kp.subst_k <= kSubstSmemK) {
+        for (int i = threadIdx.x; i < kp.subst_k * kp.subst_k; i += blockDim.x) stab[i] = __ldg(kp.subst + i);
+        __syncthreads();
+        out.subst = stab;
+    }
+    return out;
+}
+
 // SYM: uint8_t symbol codes, or uint16_t for pairs with more than 256 distinct elements
 // (tanw_set_symbol_bytes); offsets in PairDesc count symbols.
-template <bool SUBST, int VAR, typename SYM = uint8_t>
+// MULTI: every pair names its own scoring system (BatchArgs::kparams / sidx) -- the reference's
+// parameter sweep, 729 vectors over the same pages (evaluate_text_alignment.py:134-194), as ONE
+// launch; VAR is then the most general variant any system of the batch needs.
+template <bool SUBST, int VAR, typename SYM = uint8_t, bool MULTI = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
-align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
+align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp_launch)
 {
     __shared__ unsigned tiles[kWarpsPerBlock][(kTileRows + 1) * kTileStride];
+    __shared__ int stab[SUBST ? kSubstSmemK * kSubstSmemK : 1];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * kWarpsPerBlock + warp;
     uint8_t *const ptr = a.ptr_arena + (size_t)slot * (size_t)a.slot_bytes;
     int2 *const bnd = a.bnd_arena + (size_t)slot * (size_t)a.bnd_rows;
+    KParams kp = kp_launch;
+    if (SUBST) kp = stage_subst(kp_launch, stab);
 
     for (;;) {
         unsigned idx = 0;
@@ -732,6 +785,8 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
         const int p = a.order[idx];
         const PairDesc pd = a.pairs[p];
         const int n = pd.n, m = pd.m;
+        if (MULTI) kp = a.kparams[a.sidx[p]];
+        TANW_ASSERT(a.check, ptr_bytes(n, m) <= a.slot_bytes && n + 2 <= a.bnd_rows, 1);
         const SYM *T = reinterpret_cast<const SYM *>(a.sym) + pd.t_off;
         const SYM *O = reinterpret_cast<const SYM *>(a.sym) + pd.o_off;
         int cap[3];
@@ -770,6 +825,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp)
         __syncwarp();
         uint8_t *ops = a.ops + pd.ops_off;
         const int L = traceback_warp(ptr, n, m, kMaxC, ops + (size_t)n + (size_t)m, tiles[warp], lane);
+        TANW_ASSERT(a.check, L >= max(n, m) && L <= n + m, 2);
         if (lane == 0) {
             a.ops_len[p] = L;
             if (a.scores) {
@@ -813,10 +869,20 @@ __host__ __device__ inline long long line_ptr_bytes(int n, int m)
     return (n <= 0 || m <= 0) ? 0 : ((long long)n + 8) * kLineG * line_c(m);
 }
 
+// Line pairs of a chunk, sorted by descending (strip-width class, n) on the device
+// (tanw_tables.cuh): class c = pairs with strip width 4*(c+1) (cell-less pairs count as class 0).
+// Quad q of a class = its entries 4q .. 4q+3; quads never mix classes.
+struct LineClasses {
+    int start[4], count[4];      // where a class begins in the sorted list, and its size
+    int quad0[4];                // quads before the class (classes are laid out 3, 2, 1, 0)
+    int n_quads;
+};
+
 struct LineArgs {
     const uint8_t  *sym;
     const PairDesc *pairs;
-    const int4     *quads;       // four pair indices (or -1) of equal strip width, similar n
+    const int      *sorted;      // the chunk's line pairs, sorted
+    const LineClasses *classes;
     unsigned       *counter;
     int             n_quads;
     uint8_t        *ptr_arena;   // slot_bytes per 8-lane group
@@ -842,7 +908,7 @@ __device__ __forceinline__ void line_step(Strip<C> &s, LineState &ls, const KPar
     if (gl == 0) { q_in = ls.bq | kTagM; y_in = ls.bq; }        // column 0: M = Y = bg*i (:54-56)
     const int dul_in = (VAR >= 1) ? ls.q_prev : max(ls.q_prev, ls.y_prev);
     const int tch = ls.tnext;
-    if (!GUARDED || (i >= 0 && i < n)) ls.tnext = (int)__ldg(ls.tp);
+    if (!GUARDED || (i >= 0 && i < n)) ls.tnext = table_code<SUBST>((int)__ldg(ls.tp), kp);
     if (!GUARDED || (act && i >= 1 && i <= n)) {
         unsigned pw[C / 4];
         const int kfin = (GUARDED && i == n && gl == fin_lane) ? fin_k : -1;
@@ -930,6 +996,7 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
         while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // :154-158
         while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // :160-164
     }
+    __syncwarp();                       // the group's op bytes are read by all its lanes next
     return __shfl_sync(kFull, k, 0, kLineG);
 }
 
@@ -967,7 +1034,7 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
 #pragma unroll
         for (int k = 0; k < C; ++k) {
             const int c = c0 + k;
-            s.oc[k] = (act && c < m) ? (int)__ldg(O + c) : (SUBST ? 0 : 0x100);
+            s.oc[k] = (act && c < m) ? table_code<SUBST>((int)__ldg(O + c), kp) : (SUBST ? 0 : 0x100);
             const int base = kp.bg * (c + 1);                // row 0 (:57-60)
             s.W[k] = base | kTagM;
             s.Xh[k] = base | kTagX;
@@ -978,7 +1045,7 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
         ls.y_out = kNeg;
         ls.q_prev = (kp.bg * c0) | kTagM;
         ls.y_prev = kNeg;
-        ls.tnext = (gl == 0) ? (int)__ldg(T) : 0;
+        ls.tnext = (gl == 0) ? table_code<SUBST>((int)__ldg(T), kp) : 0;
         ls.tp = T + (1 - gl);
         ls.xe = kp.ex * (1 - gl);
         ls.cx = kp.ox - ls.xe;
@@ -1038,23 +1105,31 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
 
 template <bool SUBST, int VAR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
-align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
+align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp_launch)
 {
     __shared__ unsigned tiles[kWarpsPerBlock][4 * (kLineG + 1) * kLineTile];
+    __shared__ int stab[SUBST ? kSubstSmemK * kSubstSmemK : 1];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane >> 3;
     const long long slot = ((long long)blockIdx.x * kWarpsPerBlock + warp) * 4 + g;
     uint8_t *const ptr = a.ptr_arena + (size_t)slot * (size_t)a.slot_bytes;
     unsigned *const tile = tiles[warp] + g * ((kLineG + 1) * kLineTile);
+    const LineClasses lc = *a.classes;
+    KParams kp = kp_launch;
+    if (SUBST) kp = stage_subst(kp_launch, stab);
     for (;;) {
         unsigned idx = 0;
         if (lane == 0) idx = atomicAdd(a.counter, 1u);
         idx = __shfl_sync(kFull, idx, 0);
         if (idx >= (unsigned)a.n_quads) break;
-        const int4 quad = a.quads[idx];
-        const int p = (g == 0) ? quad.x : (g == 1) ? quad.y : (g == 2) ? quad.z : quad.w;
-        const int C = line_c(a.pairs[quad.x].m);             // uniform: a quad holds one strip width
+        int cls = 3;                                         // the class this quad belongs to
+        if ((int)idx >= lc.quad0[2]) cls = 2;
+        if ((int)idx >= lc.quad0[1]) cls = 1;
+        if ((int)idx >= lc.quad0[0]) cls = 0;
+        const int e = 4 * ((int)idx - lc.quad0[cls]) + g;    // this group's entry of the class
+        const int p = (e < lc.count[cls]) ? a.sorted[lc.start[cls] + e] : -1;
+        const int C = 4 * (cls + 1);                         // uniform: a quad holds one strip width
         switch (C) {
         case 4:  line_quad<4,  SUBST, VAR>(a, kp, p, ptr, tile, lane); break;
         case 8:  line_quad<8,  SUBST, VAR>(a, kp, p, ptr, tile, lane); break;
@@ -1072,7 +1147,7 @@ align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp)
 // behind it -- a wavefront over stripes.  Pointers for the whole matrix stay in HBM
 // (1 byte/cell; 8 GB for config 5), and the ordinary tile-prefetch traceback runs afterwards.
 struct LongArgs {
-    const uint8_t *T, *O;
+    const uint8_t *T, *O;  // byte addresses; symbols are SYM wide
     int n, m;              // the whole pair
     int r0, nb;            // this launch: rows r0+1 .. r0+nb (one band; r0 = 0, nb = n without banding)
     uint8_t *ptr;          // ptr_bytes(nb, m, cfull) when store != 0
@@ -1085,9 +1160,10 @@ struct LongArgs {
     int *ck_out;           // where to leave the state at row r0+nb (3*m ints) or null
     int store;             // write pointer bytes
     int *scores;           // 3 ints, written by the launch that contains row n (or null)
+    int *check;            // TANW_CHECKED builds: first failed device assertion
 };
 
-template <bool SUBST, int VAR>
+template <bool SUBST, int VAR, typename SYM = uint8_t>
 __global__ void __launch_bounds__(32, 8)
 align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
 {
@@ -1114,62 +1190,14 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
     ch.ck_out = a.ck_out;
     ch.m = m;
     ch.store = a.store != 0;
-    dispatch_pass<SUBST, VAR, true>(C, kp, a.T + a.r0, a.O, n, m, j0, !last, nullptr, nullptr,
-                                    a.ptr + (size_t)w * (size_t)pass_bytes, fin_lane, fin_k, cap, ch);
+    ch.check = a.check;
+    dispatch_pass<SUBST, VAR, true, SYM>(C, kp, reinterpret_cast<const SYM *>(a.T) + a.r0,
+                                         reinterpret_cast<const SYM *>(a.O), n, m, j0, !last, nullptr, nullptr,
+                                         a.ptr + (size_t)w * (size_t)pass_bytes, fin_lane, fin_k, cap, ch);
     if (last && (int)(threadIdx.x & 31) == fin_lane && a.scores && a.r0 + a.nb == a.n) {
         a.scores[0] = score_out(cap[0]);
         a.scores[1] = score_out(cap[1]);
         a.scores[2] = score_out(cap[2]);
-    }
-}
-
-// Column 0 of the matrices for rows r0+1 .. r0+nb as hand-over records (textSeqCompare.py:54-56:
-// M[i][0] = Y[i][0] = gap_extend * i; the Q slot carries the M tag), so that stripe 0 consumes its
-// left boundary exactly like every other stripe.
-__global__ void long_col0_kernel(int4 *rec, int nb, int r0, int bg, int epoch)
-{
-    const int r = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r <= nb) {
-        const int v = bg * (r0 + r);
-        rec[r] = make_int4(v | kTagM, epoch, v, epoch);
-    }
-}
-
-// Traceback of one band of a chained-stripe pair.  state = {x, y, st, k} persists between bands
-// (x, y in matrix coordinates); `init` starts at (n, m), `final` flushes the remainders
-// (textSeqCompare.py:154-164) and moves the op string to the start of its buffer.
-__global__ void __launch_bounds__(32)
-trace_long_kernel(const uint8_t *ptr, int n, int m, int cfull, int r0, int nb, int init, int final,
-                  int *state, uint8_t *ops, int *ops_len)
-{
-    __shared__ unsigned tile[kTileRows * kTileStride];
-    const int lane = threadIdx.x & 31;
-    uint8_t *ops_end = ops + (size_t)n + (size_t)m;
-    int x = init ? n : state[0], y = init ? m : state[1], st = init ? -1 : state[2], k = init ? 0 : state[3];
-    __syncwarp();
-    int xl = x - r0;                                       // row inside this band's pointer block
-    if (xl > 0 && y > 0) traceback_core(ptr, nb, m, cfull, ops_end, tile, lane, xl, y, st, k);
-    x = xl + r0;
-    if (!final) {
-        if (lane == 0) { state[0] = x; state[1] = y; state[2] = st; state[3] = k; }
-        return;
-    }
-    if (lane == 0) {
-        while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // :154-158
-        while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // :160-164
-        *ops_len = k;
-    }
-    const int L = __shfl_sync(kFull, k, 0);
-    const int shift = n + m - L;
-    if (shift > 0) {
-        for (int base = 0; base < L; base += 32) {
-            const int q = base + lane;
-            uint8_t v = 0;
-            if (q < L) v = __ldcg(ops + shift + q);
-            __syncwarp();
-            if (q < L) ops[q] = v;
-            __syncwarp();
-        }
     }
 }
 

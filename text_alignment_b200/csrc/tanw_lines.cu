@@ -1,0 +1,39 @@
+// tanw_lines.cu -- instantiations of the four-pairs-per-warp line kernel (align_lines_kernel).
+#include "tanw_launch.h"
+
+namespace tanw {
+
+template <bool SUBST, int VAR>
+static cudaError_t go(const LineArgs &a, const KParams &kp, int grid, cudaStream_t stream)
+{
+    align_lines_kernel<SUBST, VAR><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, kp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lines(const LineArgs &a, const KParams &kp, int var, bool subst, int grid, cudaStream_t stream)
+{
+    if (subst) {
+        switch (var) {
+        case 2:  return go<true, 2>(a, kp, grid, stream);
+        case 1:  return go<true, 1>(a, kp, grid, stream);
+        default: return go<true, 0>(a, kp, grid, stream);
+        }
+    }
+    switch (var) {
+    case 2:  return go<false, 2>(a, kp, grid, stream);
+    case 1:  return go<false, 1>(a, kp, grid, stream);
+    default: return go<false, 0>(a, kp, grid, stream);
+    }
+}
+
+int lines_blocks_per_sm()
+{
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_lines_kernel<true, 0>, kWarpsPerBlock * 32, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return occ;
+}
+
+}  // namespace tanw

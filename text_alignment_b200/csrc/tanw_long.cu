@@ -1,0 +1,92 @@
+// tanw_long.cu -- instantiations of the chained-stripe kernels (one whole-manuscript pair).
+#include "tanw_launch.h"
+
+namespace tanw {
+
+// Column 0 of the matrices for rows r0+1 .. r0+nb as hand-over records (textSeqCompare.py:54-56:
+// M[i][0] = Y[i][0] = gap_extend * i; the Q slot carries the M tag), so that stripe 0 consumes its
+// left boundary exactly like every other stripe.
+__global__ void long_col0_kernel(int4 *rec, int nb, int r0, int bg, int epoch)
+{
+    const int r = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= nb) {
+        const int v = bg * (r0 + r);
+        rec[r] = make_int4(v | kTagM, epoch, v, epoch);
+    }
+}
+
+// Traceback of one band of a chained-stripe pair.  state = {x, y, st, k} persists between bands
+// (x, y in matrix coordinates); `init` starts at (n, m), `final` flushes the remainders
+// (textSeqCompare.py:154-164) and moves the op string to the start of its buffer.
+__global__ void __launch_bounds__(32)
+trace_long_kernel(const uint8_t *ptr, const PairDesc *pd, int cfull, int r0, int nb, int init, int final,
+                  int *state, uint8_t *ops_base, int *ops_len)
+{
+    __shared__ unsigned tile[kTileRows * kTileStride];
+    const int lane = threadIdx.x & 31;
+    const int n = pd->n, m = pd->m;
+    uint8_t *ops = ops_base + pd->ops_off;
+    uint8_t *ops_end = ops + (size_t)n + (size_t)m;
+    int x = init ? n : state[0], y = init ? m : state[1], st = init ? -1 : state[2], k = init ? 0 : state[3];
+    __syncwarp();
+    int xl = x - r0;                                       // row inside this band's pointer block
+    if (xl > 0 && y > 0) traceback_core(ptr, nb, m, cfull, ops_end, tile, lane, xl, y, st, k);
+    x = xl + r0;
+    if (!final) {
+        if (lane == 0) { state[0] = x; state[1] = y; state[2] = st; state[3] = k; }
+        return;
+    }
+    if (lane == 0) {
+        while (y > 0) { ++k; *(ops_end - k) = 2; --y; }      // :154-158
+        while (x > 0) { ++k; *(ops_end - k) = 1; --x; }      // :160-164
+        *ops_len = k;
+    }
+    __syncwarp();                       // lane 0's op bytes are read by every lane next
+    const int L = __shfl_sync(kFull, k, 0);
+    const int shift = n + m - L;
+    if (shift > 0) {
+        for (int base = 0; base < L; base += 32) {
+            const int q = base + lane;
+            uint8_t v = 0;
+            if (q < L) v = __ldcg(ops + shift + q);
+            __syncwarp();
+            if (q < L) ops[q] = v;
+            __syncwarp();
+        }
+    }
+}
+
+const void *long_kernel(int var, bool subst, int sym_bytes)
+{
+    if (sym_bytes == 2)
+        return subst ? (const void *)align_long_kernel<true, 0, uint16_t> : (const void *)align_long_kernel<false, 0, uint16_t>;
+    if (subst) return (const void *)align_long_kernel<true, 0, uint8_t>;
+    return var == 2 ? (const void *)align_long_kernel<false, 2, uint8_t>
+         : var == 1 ? (const void *)align_long_kernel<false, 1, uint8_t>
+                    : (const void *)align_long_kernel<false, 0, uint8_t>;
+}
+
+int long_blocks_per_sm()
+{
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_long_kernel<true, 0, uint8_t>, 32, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return occ;
+}
+
+cudaError_t launch_long_col0(int4 *rec, int nb, int r0, int bg, int epoch, cudaStream_t stream)
+{
+    long_col0_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(rec, nb, r0, bg, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_long_trace(const uint8_t *ptr, const PairDesc *pd, int cfull, int r0, int nb, int init, int final,
+                              int *state, uint8_t *ops_base, int *ops_len, cudaStream_t stream)
+{
+    trace_long_kernel<<<1, 32, 0, stream>>>(ptr, pd, cfull, r0, nb, init, final, state, ops_base, ops_len);
+    return cudaGetLastError();
+}
+
+}  // namespace tanw

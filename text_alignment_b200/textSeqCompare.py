@@ -35,12 +35,15 @@ _contexts = {}
 _contexts_lock = threading.Lock()
 
 
-def get_context(device=0):
-    """Process-wide native context of a device (created on first use)."""
+def get_context(device=0, replica=0):
+    """Process-wide native context of a device (created on first use).  A context serialises its
+    callers (``Context.lock``); ``replica`` > 0 names further contexts on the same device, which
+    ``align_packed`` uses when its device list names one device more than once."""
+    key = (int(device), int(replica))
     with _contexts_lock:
-        ctx = _contexts.get(device)
+        ctx = _contexts.get(key)
         if ctx is None:
-            ctx = _contexts[device] = _native.Context(device)
+            ctx = _contexts[key] = _native.Context(int(device))
         return ctx
 
 
@@ -88,12 +91,23 @@ def parse_scoring_system(scoring_system):
 
 
 # ---- list <-> packed code conversion ------------------------------------------------------------
+#
+# The device sees uint8 (or uint16) codes with "equal code <=> elements compare equal".  A whole
+# batch is interned at once, so that one launch -- and, for a callable scorer, one K x K table --
+# serves all its pairs.  Two routes:
+#   * every element is a 1-character str (the production call, alignToOCR.py:273): code points,
+#     read with the CPython helper (csrc/tanw_pylist.c) or one join + encode per sequence;
+#   * anything else (the 2-character strings of the reference's demo :185-186, tuples, ...):
+#     a dict-based interner over the batch.
+
+MAX_SYMBOLS = 65536          # distinct elements per launch (uint16 codes)
+MAX_TABLE_SYMBOLS = 2048     # ... when the scorer needs a K x K table (include/tanw.h)
+
 
 class _Encoded(object):
-    """One pair as uint8 codes (uint16 when it has more than 256 distinct elements).
-    ``symbols``: distinct elements in code order (None when the codes are the elements' own code
-    points, which needs no table)."""
-    __slots__ = ('t_codes', 'o_codes', 'symbols', 't_cp', 'o_cp', 'reflexive')
+    """A batch of pairs as packed codes.  ``alphabet``: the element each code stands for, or None
+    when the codes are the elements' own code points."""
+    __slots__ = ('symbols', 't_off', 'n', 'o_off', 'm', 'alphabet', 'reflexive', 'chars')
 
 
 def _code_points(seq):
@@ -117,120 +131,159 @@ def _code_points(seq):
         return None
 
 
-MAX_SYMBOLS = 65536          # distinct elements per pair (uint16 codes)
-MAX_TABLE_SYMBOLS = 2048     # ... when the scorer is a callable (K x K table, include/tanw.h)
+def _batch_code_points(pairs, n, m):
+    """Code points of every sequence of the batch, concatenated T0 O0 T1 O1 ..., or None when some
+    element is not a 1-character str."""
+    total = int(n.sum() + m.sum())
+    cp = np.empty(max(total, 1), dtype=np.uint32)
+    helper = _native.pylist()
+    if helper is not None:
+        top = np.zeros(1, dtype=np.uint32)
+        base, ptop, fn = cp.ctypes.data, top.ctypes.data, helper.tanw_pylist_codepoints
+        at = 0
+        for t, o in pairs:
+            k = fn(t, base + 4 * at, total - at, ptop)
+            if k < 0:
+                return None
+            at += k
+            k = fn(o, base + 4 * at, total - at, ptop)
+            if k < 0:
+                return None
+            at += k
+        return cp[:total]
+    at = 0
+    for t, o in pairs:
+        for seq in (t, o):
+            c = _code_points(seq)
+            if c is None:
+                return None
+            cp[at:at + c.size] = c
+            at += c.size
+    return cp[:total]
+
+
+def _layout(n, m):
+    lens = n.astype(np.int64) + m
+    t_off = np.zeros(n.size, dtype=np.int64)
+    if n.size:
+        np.cumsum(lens[:-1], out=t_off[1:])
+    return t_off, t_off + n
 
 
 def _code_dtype(distinct, tabulated):
-    """uint8 codes while they suffice; uint16 for pairs with more distinct elements (the device
-    then runs them on the page kernel only, tanw_set_symbol_bytes)."""
+    """uint8 codes while they suffice, uint16 beyond; None when one launch cannot hold them."""
     if distinct <= 256:
         return np.uint8
-    limit = MAX_TABLE_SYMBOLS if tabulated else MAX_SYMBOLS
-    if distinct > limit:
-        raise ValueError('more than {} distinct symbols in one pair ({}); the device path cannot '
-                         'represent them'.format(limit, distinct))
-    return np.uint16
+    if distinct <= (MAX_TABLE_SYMBOLS if tabulated else MAX_SYMBOLS):
+        return np.uint16
+    return None
 
 
-def _encode_pair(transcript, ocr, need_dense):
+def _encode_batch(pairs, tabulated):
+    """-> _Encoded for the whole batch, or None when its distinct elements do not fit one launch
+    (the caller then encodes pair by pair)."""
     enc = _Encoded()
     enc.reflexive = True
-    enc.t_cp = enc.o_cp = None
-    # production case (alignToOCR.py:273: list(transcript), list(ocr)): single characters
-    t_cp = _code_points(transcript)
-    o_cp = _code_points(ocr) if t_cp is not None else None
-    if o_cp is not None:
-        enc.t_cp, enc.o_cp = t_cp, o_cp
-        top = int(max(t_cp.max() if t_cp.size else 0, o_cp.max() if o_cp.size else 0))
-        if top < 256 and not need_dense:
-            enc.t_codes = t_cp.astype(np.uint8)
-            enc.o_codes = o_cp.astype(np.uint8)
-            enc.symbols = None
+    enc.n = np.fromiter((len(t) for t, _ in pairs), dtype=np.int32, count=len(pairs))
+    enc.m = np.fromiter((len(o) for _, o in pairs), dtype=np.int32, count=len(pairs))
+    enc.t_off, enc.o_off = _layout(enc.n, enc.m)
+    cp = _batch_code_points(pairs, enc.n, enc.m)
+    enc.chars = cp is not None
+    if cp is not None:
+        if not tabulated and (cp.size == 0 or int(cp.max()) < 256):
+            enc.symbols = cp.astype(np.uint8)
+            enc.alphabet = None
             return enc
-        both = np.concatenate([t_cp, o_cp])
-        uniq, inv = np.unique(both, return_inverse=True)
-        code_t = _code_dtype(uniq.size, need_dense)
-        enc.t_codes = inv[:t_cp.size].astype(code_t)
-        enc.o_codes = inv[t_cp.size:].astype(code_t)
-        enc.symbols = [chr(c) for c in uniq.tolist()]
+        uniq, inv = np.unique(cp, return_inverse=True)
+        dt = _code_dtype(uniq.size, tabulated)
+        if dt is None:
+            return None
+        enc.symbols = inv.astype(dt)
+        enc.alphabet = [chr(c) for c in uniq.tolist()]
         return enc
-    # general elements (e.g. the 2-character strings of the reference's demo, :185-186)
-    table = {}
-    symbols = []
-    loose = []          # unhashable elements: compared with == against known representatives
+    # general elements: equal under == (and hash) -> same code; unhashable ones are compared
+    # with == against the representatives seen so far
+    table, alphabet, loose = {}, [], []
 
     def code_of(e):
         try:
             c = table.get(e)
             if c is None:
-                c = table[e] = len(symbols)
-                symbols.append(e)
+                c = table[e] = len(alphabet)
+                alphabet.append(e)
             return c
         except TypeError:
             for c, rep in loose:
                 if rep == e:
                     return c
-            c = len(symbols)
-            symbols.append(e)
+            c = len(alphabet)
+            alphabet.append(e)
             loose.append((c, e))
             return c
-    t_codes = [code_of(e) for e in transcript]
-    o_codes = [code_of(e) for e in ocr]
-    code_t = _code_dtype(len(symbols), need_dense)
-    enc.t_codes = np.asarray(t_codes, dtype=code_t)
-    enc.o_codes = np.asarray(o_codes, dtype=code_t)
-    enc.symbols = symbols
+    codes = []
+    for t, o in pairs:
+        codes.extend(code_of(e) for e in t)
+        codes.extend(code_of(e) for e in o)
+    dt = _code_dtype(len(alphabet), True)      # a non-reflexive element would need the table
+    if dt is None:
+        return None
+    enc.symbols = np.asarray(codes, dtype=dt) if codes else np.zeros(0, dtype=dt)
+    enc.alphabet = alphabet
     # a == b must mean "same code"; objects with a non-reflexive == (NaN) break that
-    for s in symbols:
-        if type(s) is not str:
+    for e in alphabet:
+        if type(e) is not str:
             try:
-                if not (s == s):
+                if not (e == e):
                     enc.reflexive = False
             except Exception:
                 enc.reflexive = False
+    if enc.reflexive and _code_dtype(len(alphabet), tabulated) is None:
+        return None
     return enc
 
 
 def _tabulate(enc, fn, match, mismatch):
-    """K x K int32 substitution table for the symbols of one pair.  Only (transcript symbol,
-    OCR symbol) combinations are evaluated -- the reference never calls the scorer on any
-    other combination (textSeqCompare.py:67)."""
-    k = len(enc.symbols)
-    tab = np.zeros((max(k, 1), max(k, 1)), dtype=np.int32)
-    t_present = np.unique(enc.t_codes).tolist()
-    o_present = np.unique(enc.o_codes).tolist()
-    for a in t_present:
-        sa = enc.symbols[a]
-        for b in o_present:
-            sb = enc.symbols[b]
-            if fn is not None:
-                tab[a, b] = _as_int(fn(sa, sb), 'scoring function value')
-            else:
-                tab[a, b] = match if sa == sb else mismatch
+    """K x K int32 substitution table for the alphabet of a batch.  Only (transcript symbol,
+    OCR symbol) combinations that meet in some pair are evaluated -- the reference never calls
+    the scorer on any other combination (textSeqCompare.py:67)."""
+    k = max(len(enc.alphabet), 1)
+    tab = np.zeros((k, k), dtype=np.int32)
+    P = enc.n.size
+    if P == 0 or enc.symbols.size == 0:
+        return tab
+    # which symbols occur in the transcript / the OCR of which pair
+    pair_of_t = np.repeat(np.arange(P), enc.n)
+    pair_of_o = np.repeat(np.arange(P), enc.m)
+    t_idx = np.repeat(enc.t_off, enc.n) + (np.arange(pair_of_t.size) - np.repeat(np.cumsum(enc.n) - enc.n, enc.n))
+    o_idx = np.repeat(enc.o_off, enc.m) + (np.arange(pair_of_o.size) - np.repeat(np.cumsum(enc.m) - enc.m, enc.m))
+    in_t = np.zeros((P, k), dtype=bool)
+    in_o = np.zeros((P, k), dtype=bool)
+    in_t[pair_of_t, enc.symbols[t_idx]] = True
+    in_o[pair_of_o, enc.symbols[o_idx]] = True
+    meet = (in_t.astype(np.float32).T @ in_o.astype(np.float32)) > 0
+    for a, b in zip(*np.nonzero(meet)):
+        sa, sb = enc.alphabet[a], enc.alphabet[b]
+        if fn is not None:
+            tab[a, b] = _as_int(fn(sa, sb), 'scoring function value')
+        else:
+            tab[a, b] = match if sa == sb else mismatch
     return tab
 
 
-def _decode(transcript, ocr, ops, enc):
-    """ops (uint8, left to right) -> (tra_align, ocr_align) lists (textSeqCompare.py:116-117,
-    :129-130, :139-140 after the reversal of :167-168)."""
-    if enc is not None and enc.t_cp is not None:
-        L = ops.size
-        tra = np.full(L, ord(GAP), dtype=np.uint32)
-        oc = np.full(L, ord(GAP), dtype=np.uint32)
-        tra[ops != 2] = enc.t_cp
-        oc[ops != 1] = enc.o_cp
-        try:        # bytes -> str -> list of 1-character strings: three times faster than view('<U1').tolist()
-            return (list(tra.tobytes().decode('utf-32-le', 'surrogatepass')),
-                    list(oc.tobytes().decode('utf-32-le', 'surrogatepass')))
-        except (ValueError, UnicodeError):
-            pass
-    it_t = iter(transcript)
-    it_o = iter(ocr)
-    ops_l = ops.tolist()
-    tra = [GAP if op == 2 else next(it_t) for op in ops_l]
-    oc = [GAP if op == 1 else next(it_o) for op in ops_l]
-    return tra, oc
+def _expand(seq, ops, gap_op):
+    """One aligned sequence (textSeqCompare.py:116-117, :129-130, :139-140 after the reversal of
+    :167-168): GAP where the op is `gap_op`, else the caller's own next element."""
+    helper = _native.pylist()
+    if helper is not None:
+        ops = np.ascontiguousarray(ops)
+        return helper.tanw_pylist_expand(seq, ops.ctypes.data, ops.size, gap_op, GAP)
+    it = iter(seq)
+    return [GAP if op == gap_op else next(it) for op in ops.tolist()]
+
+
+def _decode(transcript, ocr, ops):
+    """ops (uint8, left to right) -> (tra_align, ocr_align) lists."""
+    return _expand(transcript, ops, 2), _expand(ocr, ops, 1)
 
 
 def _align_record(transcript, ocr, ops):
@@ -257,6 +310,10 @@ def _check_list(seq, name):
     if not isinstance(seq, list):
         seq + [' ']          # raises TypeError for str / tuple exactly as the reference does
         raise TypeError('{} must be a list'.format(name))
+
+
+def _score_tuple(row):
+    return tuple(None if v == _native.NEG_INF else int(v) for v in row.tolist())
 
 
 # ---- public API ---------------------------------------------------------------------------------
@@ -287,6 +344,17 @@ def perform_alignment(transcript, ocr, scoring_system=None, verbose=False, devic
     return (tra, oc)
 
 
+def _align_encoded(enc, fn, numeric, boundary, devices):
+    """One launch per device for an encoded batch -> (ops, ops_off, ops_len, scores)."""
+    match, mismatch, gox, goy, gex, gey = numeric
+    if fn is not None or not enc.reflexive:
+        tab = _tabulate(enc, fn, match, mismatch)
+        params, subst = (0, 0, gox, goy, gex, gey, boundary), tab
+    else:
+        params, subst = (match, mismatch, gox, goy, gex, gey, boundary), None
+    return align_packed(enc.symbols, enc.t_off, enc.n, enc.o_off, enc.m, params, subst=subst, devices=devices)
+
+
 def perform_alignment_batch(pairs, scoring_system=None, devices=None, return_scores=False, _keep_ops=False):
     """Align many (transcript, ocr) list pairs in one launch per device.
 
@@ -299,109 +367,68 @@ def perform_alignment_batch(pairs, scoring_system=None, devices=None, return_sco
     for t, o in pairs:
         _check_list(t, 'transcript')
         _check_list(o, 'ocr')
-    encs = [_encode_pair(t, o, need_dense=fn is not None) for t, o in pairs]
-    need_table = [fn is not None or not e.reflexive for e in encs]
-    results = [None] * len(pairs)
-    plain = [k for k in range(len(pairs)) if not need_table[k]]
-    # pairs with 16-bit codes run on the page kernel only: keep them out of the others' launch
-    for group in ([k for k in plain if encs[k].t_codes.dtype == np.uint8],
-                  [k for k in plain if encs[k].t_codes.dtype != np.uint8]):
-        if group:
-            out = _run_group([encs[k] for k in group], (match, mismatch, gox, goy, gex, gey, boundary), None, devices)
-            for k, r in zip(group, out):
-                results[k] = r
-    for k in range(len(pairs)):
-        if need_table[k]:
-            # a substitution table is specific to the pair's symbol set: one launch per pair
-            if encs[k].symbols is None:
-                encs[k] = _encode_pair(pairs[k][0], pairs[k][1], need_dense=True)
-            tab = _tabulate(encs[k], fn, match, mismatch)
-            results[k] = _run_group([encs[k]], (0, 0, gox, goy, gex, gey, boundary), tab, devices)[0]
-    final = []
-    for k, (ops, score) in enumerate(results):
-        tra, oc = _decode(pairs[k][0], pairs[k][1], ops, encs[k])
-        item = (tra, oc)
-        if return_scores:
-            item = item + (score,)
-        if _keep_ops:
-            item = item + (ops,)
-        final.append(item)
+    if not pairs:
+        return []
+    numeric = (match, mismatch, gox, goy, gex, gey)
+    enc = _encode_batch(pairs, tabulated=fn is not None)
+    if enc is not None:
+        groups = [(range(len(pairs)), _align_encoded(enc, fn, numeric, boundary, devices))]
+    else:
+        # more distinct elements than one launch can code: pair by pair (each has its own alphabet)
+        groups = []
+        for k, pr in enumerate(pairs):
+            one = _encode_batch([pr], tabulated=fn is not None)
+            if one is None:
+                raise ValueError('more than {} distinct symbols in one pair; the device path cannot '
+                                 'represent them'.format(MAX_TABLE_SYMBOLS if fn is not None else MAX_SYMBOLS))
+            groups.append(([k], _align_encoded(one, fn, numeric, boundary, devices)))
+    final = [None] * len(pairs)
+    for members, (ops, ops_off, ops_len, scores) in groups:
+        for j, k in enumerate(members):
+            o = ops[ops_off[j]:ops_off[j] + ops_len[j]]
+            item = _decode(pairs[k][0], pairs[k][1], o)
+            if return_scores:
+                item = item + (_score_tuple(scores[j]),)
+            if _keep_ops:
+                item = item + (o,)
+            final[k] = item
     return final
 
 
 def perform_alignment_sweep(pairs, scoring_systems, device=0, return_scores=False):
     """The reference's parameter sweep (evaluate_text_alignment.py:134-198 re-aligns the same
-    pages under 729 scoring vectors): the pairs are encoded and uploaded once, then every
-    numeric scoring system costs one launch.  Returns one result list (as
-    ``perform_alignment_batch``) per scoring system."""
+    pages under 729 scoring vectors) as ONE launch: the pairs are encoded and uploaded once and
+    every (scoring system, pair) combination is a pair of the batch with its own parameters
+    (tanw_align_batch_multi).  Returns one result list (as ``perform_alignment_batch``) per
+    scoring system."""
     pairs = list(pairs)
     for t, o in pairs:
         _check_list(t, 'transcript')
         _check_list(o, 'ocr')
+    scoring_systems = list(scoring_systems)
     parsed = [parse_scoring_system(s) for s in scoring_systems]
-    if any(p[0] is not None for p in parsed):
-        return [perform_alignment_batch(pairs, s, devices=[device], return_scores=return_scores)
-                for s in scoring_systems]
     boundary = _as_int(gap_extend, 'gap_extend')
-    encs = [_encode_pair(t, o, need_dense=False) for t, o in pairs]
-    if not all(e.reflexive for e in encs):
+    enc = _encode_batch(pairs, tabulated=False) if pairs and not any(p[0] is not None for p in parsed) else None
+    if enc is None or not enc.reflexive or enc.symbols.dtype != np.uint8:
+        # callables, or alphabets beyond 8-bit codes: one batch per scoring system
         return [perform_alignment_batch(pairs, s, devices=[device], return_scores=return_scores)
                 for s in scoring_systems]
-    symbols, t_off, n, o_off, m = _pack_encoded(encs)
+    P, S = len(pairs), len(parsed)
+    systems = [(mt, mi, gox, goy, gex, gey, boundary) for _, mt, mi, gox, goy, gex, gey in parsed]
     ctx = get_context(device)
+    ops, ops_off, ops_len, scores = ctx.align_batch_multi(
+        enc.symbols, np.tile(enc.t_off, S), np.tile(enc.n, S), np.tile(enc.o_off, S), np.tile(enc.m, S),
+        systems, np.repeat(np.arange(S, dtype=np.int32), P))
     out = []
-    for k, (_, match, mismatch, gox, goy, gex, gey) in enumerate(parsed):
-        scoring = ctx.make_scoring(match, mismatch, gox, goy, gex, gey, boundary)
-        if k == 0:
-            ctx.prepare(symbols, t_off, n, o_off, m, scoring)
-        else:
-            ctx.rescore(scoring)
-        ctx.run()
-        ops, ops_off, ops_len, scores = ctx.fetch()
+    for k in range(S):
         res = []
-        for i in range(len(pairs)):
-            tra, oc = _decode(pairs[i][0], pairs[i][1], ops[ops_off[i]:ops_off[i] + ops_len[i]], encs[i])
-            item = (tra, oc)
+        for i in range(P):
+            j = k * P + i
+            item = _decode(pairs[i][0], pairs[i][1], ops[ops_off[j]:ops_off[j] + ops_len[j]])
             if return_scores:
-                item += (tuple(None if v == _native.NEG_INF else int(v) for v in scores[i].tolist()),)
+                item += (_score_tuple(scores[j]),)
             res.append(item)
         out.append(res)
-    return out
-
-
-def _pack_encoded(encs):
-    n = np.asarray([e.t_codes.size for e in encs], dtype=np.int32)
-    m = np.asarray([e.o_codes.size for e in encs], dtype=np.int32)
-    parts = []
-    for e in encs:
-        parts.append(e.t_codes)
-        parts.append(e.o_codes)
-    symbols = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
-    lens = n.astype(np.int64) + m.astype(np.int64)
-    t_off = np.zeros(len(encs), dtype=np.int64)
-    if len(encs):
-        np.cumsum(lens[:-1], out=t_off[1:])
-    return symbols, t_off, n, t_off + n, m
-
-
-def _run_group(encs, params, subst, devices):
-    n = np.asarray([e.t_codes.size for e in encs], dtype=np.int32)
-    m = np.asarray([e.o_codes.size for e in encs], dtype=np.int32)
-    parts = []
-    for e in encs:
-        parts.append(e.t_codes)
-        parts.append(e.o_codes)
-    symbols = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
-    lens = n.astype(np.int64) + m.astype(np.int64)
-    t_off = np.zeros(len(encs), dtype=np.int64)
-    if len(encs):
-        np.cumsum(lens[:-1], out=t_off[1:])
-    o_off = t_off + n
-    ops, ops_off, ops_len, scores = align_packed(symbols, t_off, n, o_off, m, params, subst=subst, devices=devices)
-    out = []
-    for k in range(len(encs)):
-        sc = tuple(None if v == _native.NEG_INF else int(v) for v in scores[k].tolist())
-        out.append((ops[ops_off[k]:ops_off[k] + ops_len[k]], sc))
     return out
 
 
@@ -445,7 +472,7 @@ def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, 
     def work(d):
         lo, hi = int(bounds[d]), int(bounds[d + 1])
         try:
-            ctx = get_context(devices[d])
+            ctx = get_context(devices[d], replica=devices[:d].count(devices[d]))
             sub_sym, sub_t, sub_o = _rebase(symbols, t_off[lo:hi], n[lo:hi], o_off[lo:hi], m[lo:hi])
             outs[d] = ctx.align_batch(sub_sym, sub_t, n[lo:hi], sub_o, m[lo:hi],
                                       ctx.make_scoring(*params, subst=subst), want_scores=want_scores)
