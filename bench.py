@@ -663,6 +663,31 @@ def main():
                     what='perform_alignment_batch on Python lists: interning to uint8 codes, one launch, '
                          'op strings back to two lists per page; single_call_ms = perform_alignment on one page')
 
+    # ---- the consumer either side of the path: object path vs array path ----------------
+    consumer = None
+    if rank == 0 and args.workload == 'c2' and not args.no_others:
+        from text_alignment_b200 import alignToOCR as atocr, synth
+        cpages = [synth.make_page(70000 + k, 1200, 1500) for k in range(200)]
+        arrays = []
+        for t, boxes in cpages:
+            arrays.append((t, ''.join(c for c, _, _ in boxes),
+                           np.array([[ul[0], ul[1], lr[0], lr[1]] for _, ul, lr in boxes], dtype=np.int32)))
+        atocr.boxes_for_pages_arrays(arrays[:8], devices=[h.local_rank])
+        s0 = time.perf_counter()
+        got = atocr.boxes_for_pages_arrays(arrays, devices=[h.local_rank])
+        s1 = time.perf_counter()
+        objs = [(t, [atocr.CharBox(c, ul, lr) for c, ul, lr in boxes]) for t, boxes in cpages[:16]]
+        s2 = time.perf_counter()
+        ref = atocr.boxes_for_pages(objs, devices=[h.local_rank])
+        s3 = time.perf_counter()
+        same = all([b.char for b in r[0]] == g[0] and [[b.ulx, b.uly, b.lrx, b.lry] for b in r[0]] == g[1].tolist()
+                   for r, g in zip(ref, got))
+        consumer = dict(pages=len(arrays), array_path_ms_per_page=(s1 - s0) * 1e3 / len(arrays),
+                        object_path_ms_per_page=(s3 - s2) * 1e3 / len(objs), identical=bool(same),
+                        what='transcript + OCR character boxes -> syllable boxes (alignToOCR.py:247-324) for c2-sized '
+                             'pages, alignment on the device: boxes_for_pages_arrays (native, arrays) vs boxes_for_pages '
+                             '(CharBox objects + one regex per syllable, as the reference)')
+
     # ---- the other BASELINE configs, short legs ------------------------------------------------------
     others = None
     if not args.no_others:
@@ -730,6 +755,8 @@ def main():
             clocks=clocks)
         if shim:
             line['python_list_shim'] = shim
+        if consumer:
+            line['consumer'] = consumer
         if others is not None:
             line['others'] = others
         if sharded is not None:

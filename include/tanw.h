@@ -205,6 +205,42 @@ int  tanw_stream_handle(tanw_ctx *ctx, uint64_t *out);
  * Uses the context's scratch buffers: a prepared batch must be prepared again afterwards. */
 int  tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s);
 
+/* ---- the steps either side of the alignment, on packed arrays (host code, no context) -------------
+ * OCRopus .llocs records in, syllable boxes / Rodan JSON out, without building a
+ * Python object per character.  All three return TANW_OK or a TANW_E_* code with the message in
+ * tanw_consumer_last_error() (thread-local). */
+const char *tanw_consumer_last_error(void);
+
+/* One text line of `ocropus-rpred --llocs` output (alignToOCR.py:153-182): UTF-8 records
+ * "<character> TAB <x of its RIGHT edge inside the strip> NEWLINE".  A character's box runs from
+ * the previous record's x to its own (np.round(x + x_min), half to even) over the strip's full
+ * height; records whose character is '~' or empty advance x but are dropped (:171-173).  Writes the
+ * code point and (ulx, uly, lrx, lry) of every kept character; *n_out = their number (also when
+ * `capacity` was too small: TANW_E_NOMEM, call again). */
+int  tanw_parse_llocs(const char *text, int64_t text_len, int32_t x_min, int32_t y_min, int32_t y_max,
+                      uint32_t *chars, int32_t *boxes, int64_t capacity, int64_t *n_out);
+
+/* alignToOCR.py:285-324 for many pages at once.  Per page: its op string (as tanw_align_batch
+ * returns it), its syllables as [first, one-past-last) transcript indices (syl_bounds, 2 ints per
+ * syllable, ascending; page pg owns syllables syl_off[pg] .. syl_off[pg+1]) and the boxes of its
+ * OCR characters (4 ints per character; page pg owns characters box_off[pg] .. box_off[pg+1], which
+ * must be as many as the op string consumes -- the reference's assertion at :291).  For every
+ * syllable: out_has = 0 if no OCR character is aligned to it (:313), else its box in out_boxes
+ * (union of the aligned characters' boxes, lowest text line only, :318-324).  Equivalent to the
+ * reference's regular-expression search when no transcript character is a regex metacharacter
+ * or '_' (the Python wrapper checks and otherwise keeps the regex). */
+int  tanw_syllable_boxes(int64_t n_pages, const uint8_t *ops, const int64_t *ops_off, const int32_t *ops_len,
+                         const int32_t *syl_bounds, const int64_t *syl_off,
+                         const int32_t *boxes, const int64_t *box_off,
+                         int32_t *out_boxes, uint8_t *out_has);
+
+/* alignToOCR.to_JSON_dict (:333-351) serialised as json.dumps writes it: syllable s is the UTF-8
+ * bytes syl_utf8[syl_text_off[s] .. syl_text_off[s+1]); syllables without a box are left out;
+ * `median_line_spacing` is the number already formatted by the caller.  *out_len = bytes needed. */
+int  tanw_boxes_to_json(const char *syl_utf8, const int64_t *syl_text_off, int64_t n_syl,
+                        const int32_t *syl_boxes, const uint8_t *has_box, const char *median_line_spacing,
+                        char *out, int64_t capacity, int64_t *out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,7 @@ def test_live_reference_process_100_pages(monkeypatch):
     import make_golden
     A = ref_loader.load_aligntoocr()
     monkeypatch.setattr(atocr.tsc, 'perform_alignment_batch', _oracle_batch)
+    monkeypatch.setattr(atocr.tsc, 'align_strings', _oracle_align_strings)
     rng = random.Random(12)
     for k in range(100):
         n = rng.randint(40, 110)
@@ -108,6 +109,8 @@ def test_live_reference_process_100_pages(monkeypatch):
         got, chars, _, _ = atocr.boxes_for_page(t, [atocr.CharBox(c, ul, lr) for c, ul, lr in boxes], params)
         assert _as_tuples(got) == _as_tuples(ref_boxes), (k, t)
         assert [c.char for c in chars] == [c.char for c in ref_chars]
+        arr = atocr.boxes_for_pages_arrays([(t,) + _page_arrays(boxes)], params)[0]       # the array path too
+        assert _arrays_as_tuples(arr) == _as_tuples(ref_boxes), (k, t)
 
 
 @pytest.mark.gpu
@@ -162,3 +165,159 @@ def test_parse_llocs_matches_reference_ocr_reader(tmp_path, monkeypatch):
     got = atocr.read_llocs_files([str(tmp_path / 'wk' / '_{}.llocs'.format(i)) for i in range(2)],
                                  [(s.offset_x, s.offset_y, s.height) for s in strips])
     assert [(c.char, tuple(c.ul), tuple(c.lr)) for c in ref] == [(c.char, c.ul, c.lr) for c in got]
+
+
+# ---- the same consumer on packed arrays (native: csrc/tanw_consumer.cu) ---------------------------
+
+def _page_arrays(boxes):
+    import numpy as np
+    ocr = ''.join(c for c, _, _ in boxes)
+    arr = np.array([[ul[0], ul[1], lr[0], lr[1]] for _, ul, lr in boxes], dtype=np.int32).reshape(-1, 4)
+    return ocr, arr
+
+
+def _oracle_align_strings(pairs, scoring_system=None, devices=None):
+    """Stand-in for textSeqCompare.align_strings: op strings from the CPU oracle."""
+    import numpy as np
+    from oracle import nw_oracle
+    ops, off, lens = [], [0], []
+    for t, o in pairs:
+        tra, ocr = nw_oracle.perform_alignment(list(t), list(o), scoring_system)
+        # '_' in an aligned sequence is a gap unless the other one has a gap there too (never both)
+        it_t, it_o = iter(t), iter(o)
+        row = []
+        x = y = 0
+        for a, b in zip(tra, ocr):
+            if b == '_' and not (y < len(o) and o[y] == '_' and a == '_'):
+                row.append(1); x += 1
+            elif a == '_' and not (x < len(t) and t[x] == '_'):
+                row.append(2); y += 1
+            else:
+                row.append(0); x += 1; y += 1
+        del it_t, it_o
+        ops += row + [9] * (len(t) + len(o) - len(row))
+        lens.append(len(row))
+        off.append(off[-1] + len(t) + len(o))
+    return np.array(ops, dtype=np.uint8), np.array(off[:-1], dtype=np.int64), np.array(lens, dtype=np.int32)
+
+
+def _arrays_as_tuples(res):
+    syls, boxes = res
+    return [[s, [int(b[0]), int(b[1])], [int(b[2]), int(b[3])]] for s, b in zip(syls, boxes.tolist())]
+
+
+def test_syllable_spans_are_the_syllables_in_place():
+    import numpy as np
+    for text in ['gloria in excelsis deo', 'a', '', '  double  spaces here ', 'quaecumque ejus michi euouae cuius']:
+        syls, bounds = atocr.syllable_spans(text)
+        assert syls == latsyl.syllabify_text(text)
+        assert [text[a:b] for a, b in bounds.tolist()] == syls
+        assert bounds.dtype == np.int32
+    assert atocr.regex_free('gloria in excelsis') and atocr.regex_free('') and atocr.regex_free('dūs 12')
+    assert not atocr.regex_free('glo.ria') and not atocr.regex_free('a_b') and not atocr.regex_free('quid?')
+
+
+def test_array_consumer_golden_with_oracle_aligner(golden, monkeypatch):
+    monkeypatch.setattr(atocr.tsc, 'align_strings', _oracle_align_strings)
+    monkeypatch.setattr(atocr.tsc, 'perform_alignment_batch', _oracle_batch)
+    default = [p for p in golden['pages'] if p['params'] is None]
+    out = atocr.boxes_for_pages_arrays([(p['transcript'],) + _page_arrays(p['boxes']) for p in default])
+    assert [_arrays_as_tuples(o) for o in out] == [p['syl_boxes'] for p in default]
+    for page in golden['pages']:
+        got = atocr.boxes_for_pages_arrays([(page['transcript'],) + _page_arrays(page['boxes'])], page['params'])[0]
+        assert _arrays_as_tuples(got) == page['syl_boxes'], page['seed']
+
+
+def test_array_consumer_equals_object_path_on_odd_pages(monkeypatch):
+    """Multi-line syllables (lowest line wins), syllables aligned to nothing, abbreviations, and a
+    transcript with a regex metacharacter (which must take the object path)."""
+    import numpy as np
+    monkeypatch.setattr(atocr.tsc, 'align_strings', _oracle_align_strings)
+    monkeypatch.setattr(atocr.tsc, 'perform_alignment_batch', _oracle_batch)
+    rng = random.Random(5)
+    pages = []
+    for k in range(40):
+        n = rng.randint(30, 90)
+        t, boxes = synth.make_page(41000 + k, n, int(n * rng.uniform(0.5, 1.7)), 1, 7, abbreviations=k % 2 == 0)
+        if k % 5 == 0:
+            t = t.replace(' ', '. ', 1)                   # a metacharacter: regex path
+        boxes = [(c, (ul[0], ul[1] + (7 if rng.random() < 0.1 else 0)), lr) for c, ul, lr in boxes]   # ragged lines
+        pages.append((t, boxes))
+    want = [atocr.boxes_for_page(t, [atocr.CharBox(c, ul, lr) for c, ul, lr in boxes])[0] for t, boxes in pages]
+    got = atocr.boxes_for_pages_arrays([(t,) + _page_arrays(boxes) for t, boxes in pages])
+    for w, g in zip(want, got):
+        assert _as_tuples(w) == _arrays_as_tuples(g)
+        assert g[1].dtype == np.int32
+
+
+def test_native_llocs_reader_equals_python_reader():
+    import numpy as np
+    from text_alignment_b200 import _native
+    text = u''.join(LLOCS).encode('utf-8')
+    cps, boxes = _native.parse_llocs(text, 100, 50, 110)
+    chars, _ = atocr.parse_llocs(LLOCS, 100, 50, 110)
+    assert ''.join(map(chr, cps.tolist())) == ''.join(c.char for c in chars)
+    assert boxes.tolist() == [[c.ulx, c.uly, c.lrx, c.lry] for c in chars]
+    # half-to-even rounding as np.round, CRLF line ends, a last record without newline
+    cps, boxes = _native.parse_llocs(b'a\t0.5\r\nb\t1.5\r\nc\t2.5', 0, 0, 9)
+    assert boxes[:, 2].tolist() == [int(np.round(v)) for v in (0.5, 1.5, 2.5)] == [0, 2, 2]
+    ocr, arr = atocr.page_from_llocs([text, b'd\t9.5\nn\t19.5\ns\t30.2\n~\t31.0\n'], [(100, 50, 60), (90, 190, 58)])
+    assert ocr == u'glorūadns' and arr.shape == (9, 4) and arr[6].tolist() == [90, 190, 100, 248]
+    for bad in (b'a\n', b'ab\t3\n', b'a\tx\n', b'\xff\t3\n'):
+        with pytest.raises(ValueError):
+            _native.parse_llocs(bad, 0, 0, 1)
+
+
+def test_native_json_equals_json_dumps():
+    import json
+    import numpy as np
+    syls = ['glo', u'dūs', 'a"b\\', u'\U0001d11e', 'x\ty']
+    boxes = np.array([[100, 200, 154, 260], [-3, 0, 7, 9], [1, 2, 3, 4], [5, 6, 7, 8], [9, 9, 9, 9]], dtype=np.int32)
+    peaks = [100, 240, 380, 521]
+    want = json.dumps(atocr.to_JSON_dict([atocr.CharBox(s, (b[0], b[1]), (b[2], b[3])) for s, b in zip(syls, boxes.tolist())], peaks))
+    assert atocr.to_JSON_bytes(syls, boxes, peaks) == want.encode()
+    assert json.loads(atocr.to_JSON_bytes([], np.zeros((0, 4), np.int32), peaks)) == {'median_line_spacing': 140.5, 'syl_boxes': []}
+
+
+def test_native_syllable_boxes_refuses_inconsistent_pages():
+    import numpy as np
+    from text_alignment_b200 import _native
+    ops = np.array([0, 0, 1, 2], dtype=np.uint8)
+    bounds = np.array([[0, 2], [2, 3]], dtype=np.int32)
+    boxes = np.array([[0, 0, 5, 5], [5, 0, 9, 5], [9, 0, 12, 5]], dtype=np.int32)
+    out, has = _native.syllable_boxes(ops, [0], [4], bounds, [0, 2], boxes, [0, 3])
+    assert out.tolist() == [[0, 0, 9, 5], [0, 0, 0, 0]] and has.tolist() == [True, False]
+    with pytest.raises(AssertionError):                      # one OCR box too many (alignToOCR.py:291)
+        _native.syllable_boxes(ops, [0], [4], bounds, [0, 2], np.vstack([boxes, boxes[:1]]), [0, 4])
+    with pytest.raises(ValueError):                          # a syllable beyond the transcript
+        _native.syllable_boxes(ops, [0], [4], np.array([[0, 2], [2, 5]], np.int32), [0, 2], boxes, [0, 3])
+
+
+@pytest.mark.gpu
+def test_array_consumer_on_gpu_llocs_to_json(golden):
+    """.llocs bytes in, JSON bytes out, alignment on the device, no CharBox anywhere: equal to the
+    object path on the same pages (which equals the reference's process(), see above)."""
+    import json
+    pages = [p for p in golden['pages'] if p['params'] is None]
+    arrays = []
+    for p in pages:
+        # one .llocs "file" per text line of the page, rebuilt from the golden boxes
+        lines = {}
+        for c, ul, lr in p['boxes']:
+            lines.setdefault((ul[1], lr[1]), []).append((c, ul[0], lr[0]))
+        llocs, strips = [], []
+        for (y0, y1), recs in sorted(lines.items()):
+            x0 = recs[0][1]
+            llocs.append(u''.join(u'{}\t{}\n'.format(c, float(x1 - x0)) for c, _, x1 in recs).encode('utf-8'))
+            strips.append((x0, y0, y1 - y0))
+        ocr, boxes = atocr.page_from_llocs(llocs, strips)
+        assert ocr == ''.join(c for c, _, _ in p['boxes'])
+        assert boxes.tolist() == [[ul[0], ul[1], lr[0], lr[1]] for _, ul, lr in p['boxes']]
+        arrays.append((p['transcript'], ocr, boxes))
+    out = atocr.boxes_for_pages_arrays(arrays)
+    assert [_arrays_as_tuples(o) for o in out] == [p['syl_boxes'] for p in pages]
+    peaks = [200, 340, 480, 620]
+    for (syls, boxes), p in zip(out, pages):
+        want = json.dumps({'median_line_spacing': 140.0,
+                           'syl_boxes': [{'syl': s, 'ul': ul, 'lr': lr} for s, ul, lr in p['syl_boxes']]})
+        assert atocr.to_JSON_bytes(syls, boxes, peaks) == want.encode()

@@ -67,6 +67,12 @@ SIGNATURES = {
     'tanw_sync': (ctypes.c_int, [_VOIDP]),
     'tanw_last_timing': (ctypes.c_int, [_VOIDP, ctypes.POINTER(Timing)]),
     'tanw_stream_handle': (ctypes.c_int, [_VOIDP, ctypes.POINTER(ctypes.c_uint64)]),
+    'tanw_consumer_last_error': (ctypes.c_char_p, []),
+    'tanw_parse_llocs': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.POINTER(ctypes.c_uint32), _i32p, ctypes.c_int64, _i64p]),
+    'tanw_syllable_boxes': (ctypes.c_int, [ctypes.c_int64, _u8p, _i64p, _i32p, _i32p, _i64p, _i32p, _i64p, _i32p, _u8p]),
+    'tanw_boxes_to_json': (ctypes.c_int, [ctypes.c_char_p, _i64p, ctypes.c_int64, _i32p, _u8p, ctypes.c_char_p,
+                                          ctypes.c_char_p, ctypes.c_int64, _i64p]),
     'tanw_measure_int32_peak': (ctypes.c_int, [_VOIDP, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 }
 
@@ -137,6 +143,66 @@ def device_info(device=0):
     return dict(name=info.name.decode(), cc=(info.cc_major, info.cc_minor), sm_count=info.sm_count,
                 clock_khz=info.clock_khz, total_mem_bytes=info.total_mem_bytes,
                 free_mem_bytes=info.free_mem_bytes)
+
+
+def _consumer_check(rc):
+    if rc:
+        msg = load().tanw_consumer_last_error().decode()
+        if rc == 5:
+            raise MemoryError(msg)
+        if 'all_chars not same length' in msg:
+            raise AssertionError(msg)          # the reference's own assertion (alignToOCR.py:291)
+        raise ValueError(msg)
+
+
+def parse_llocs(text, x_min, y_min, y_max):
+    """One .llocs text line (bytes) -> (code points uint32[k], boxes int32[k, 4])."""
+    lib = load()
+    cap = text.count(b'\n') + 2
+    chars = np.empty(cap, dtype=np.uint32)
+    boxes = np.empty((cap, 4), dtype=np.int32)
+    k = ctypes.c_int64(0)
+    _consumer_check(lib.tanw_parse_llocs(text, len(text), int(x_min), int(y_min), int(y_max),
+                                         chars.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), _ptr(boxes, _i32p), cap,
+                                         ctypes.byref(k)))
+    return chars[:k.value], boxes[:k.value]
+
+
+def syllable_boxes(ops, ops_off, ops_len, syl_bounds, syl_off, boxes, box_off):
+    """Many pages at once -> (boxes int32[S, 4], has_box bool[S]) for all S syllables."""
+    lib = load()
+    ops = np.ascontiguousarray(ops, dtype=np.uint8)
+    ops_off = np.ascontiguousarray(ops_off, dtype=np.int64)
+    ops_len = np.ascontiguousarray(ops_len, dtype=np.int32)
+    syl_bounds = np.ascontiguousarray(syl_bounds, dtype=np.int32)
+    syl_off = np.ascontiguousarray(syl_off, dtype=np.int64)
+    boxes = np.ascontiguousarray(boxes, dtype=np.int32)
+    box_off = np.ascontiguousarray(box_off, dtype=np.int64)
+    S = int(syl_off[-1]) if syl_off.size else 0
+    out = np.zeros((max(S, 1), 4), dtype=np.int32)
+    has = np.zeros(max(S, 1), dtype=np.uint8)
+    _consumer_check(lib.tanw_syllable_boxes(int(ops_len.size), _ptr(ops, _u8p), _ptr(ops_off, _i64p), _ptr(ops_len, _i32p),
+                                            _ptr(syl_bounds, _i32p), _ptr(syl_off, _i64p), _ptr(boxes, _i32p),
+                                            _ptr(box_off, _i64p), _ptr(out, _i32p), _ptr(has, _u8p)))
+    return out[:S], has[:S].astype(bool)
+
+
+def boxes_to_json(syllables, syl_boxes, has_box, median_line_spacing):
+    """JSON bytes of alignToOCR.to_JSON_dict, written natively (no dict, no per-box objects)."""
+    lib = load()
+    enc = [s.encode('utf-8') for s in syllables]
+    text = b''.join(enc)
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        np.cumsum(np.fromiter(map(len, enc), dtype=np.int64, count=len(enc)), out=off[1:])
+    syl_boxes = np.ascontiguousarray(syl_boxes, dtype=np.int32)
+    has = np.ascontiguousarray(has_box, dtype=np.uint8)
+    cap = 96 * int(has.sum()) + 3 * len(text) + 128
+    buf = ctypes.create_string_buffer(cap)
+    k = ctypes.c_int64(0)
+    _consumer_check(lib.tanw_boxes_to_json(text, _ptr(off, _i64p), len(enc), _ptr(syl_boxes, _i32p), _ptr(has, _u8p),
+                                           repr(float(median_line_spacing)).encode(), buf, cap, ctypes.byref(k)))
+    return buf.raw[:k.value]
 
 
 class Context(object):

@@ -179,3 +179,138 @@ def read_llocs_files(paths, strips):
             chars, _ = parse_llocs(list(f), off_x, off_y, off_y + height)
         all_chars += chars
     return all_chars
+
+
+# ---- the same consumer on packed arrays ---------------------------
+#
+# The object path above builds ~3 000 CharBox objects and runs ~400 regular-expression searches per
+# page (about 12 ms per page in CPython) behind an aligner that needs a microsecond per page.  The
+# array path keeps a page as (transcript str, OCR str, boxes int32[k, 4]) and does the per-column
+# work natively (csrc/tanw_consumer.cu): op strings straight from the device batch, syllable
+# spans as transcript index ranges, boxes by segmented min/max.  Results are identical to the
+# object path (tests/test_consumer.py checks both against the reference's own process()).
+
+import functools
+import json
+
+from . import _native
+
+
+@functools.lru_cache(maxsize=1 << 16)
+def _word_syllables(word):
+    """syllabify_word, memoised: chant texts repeat a small vocabulary."""
+    return tuple(latsyl.syllabify_word(word))
+
+
+def regex_free(transcript):
+    """True when the reference's per-syllable regular expression (alignToOCR.py:297-309) reduces
+    to "the columns from the syllable's first letter to its last": every character is a letter,
+    a digit or a space -- no regex metacharacter and no gap symbol."""
+    body = transcript.replace(' ', '')
+    return body == '' or body.isalnum()
+
+
+def syllable_spans(transcript):
+    """-> (syllables, bounds int32[S, 2]): syllable s is transcript[bounds[s, 0]:bounds[s, 1]].
+    Words are what ``split(' ')`` gives (latinSyllabification.py:171); a word's syllables are
+    consecutive pieces of it (None is returned if that ever fails to hold, and the caller keeps
+    the regular-expression path)."""
+    words = transcript.split(' ')
+    per_word = [_word_syllables(w) for w in words]
+    syls = [s for ws in per_word for s in ws]
+    S = len(syls)
+    if S == 0:
+        return syls, np.zeros((0, 2), np.int32)
+    counts = np.fromiter(map(len, per_word), dtype=np.int64, count=len(words))
+    lens = np.fromiter(map(len, syls), dtype=np.int64, count=S)
+    word_lens = np.fromiter(map(len, words), dtype=np.int64, count=len(words))
+    if lens.min() < 1 or not np.array_equal(np.add.reduceat(np.append(lens, 0), np.minimum(np.cumsum(counts) - counts, S))
+                                            * (counts > 0), word_lens * (counts > 0)) or np.any((counts == 0) & (word_lens > 0)):
+        return None
+    word_start = np.cumsum(word_lens + 1) - (word_lens + 1)     # after the words and single spaces before it
+    excl = np.cumsum(lens) - lens                               # letters of all syllables before this one
+    first = np.minimum(np.cumsum(counts) - counts, S - 1)       # a word's first syllable
+    starts = np.repeat(word_start - excl[first], counts) + excl
+    return syls, np.stack([starts, starts + lens], axis=1).astype(np.int32)
+
+
+def expand_abbreviations_arrays(ocr, boxes, abbreviations=None):
+    """alignToOCR.py:251-264 on (OCR string, boxes int32[k, 4]): same replacements in the same
+    order as ``expand_abbreviations``; every expanded letter inherits the box of the abbreviation
+    character its segment stands for."""
+    abbreviations = latsyl.abbreviations if abbreviations is None else abbreviations
+    src = None                                  # index of the box each current character uses
+    for abb, segments in abbreviations.items():
+        while True:
+            idx = ocr.find(abb)
+            if idx == -1:
+                break
+            if src is None:
+                src = list(range(len(ocr)))
+            ins = ''.join(segments)
+            ins_src = [src[idx + i] for i, seg in enumerate(segments) for _ in seg]
+            ocr = ocr[:idx] + ins + ocr[idx + len(abb):]
+            src = src[:idx] + ins_src + src[idx + len(abb):]
+    if src is None:
+        return ocr, boxes
+    return ocr, np.ascontiguousarray(np.asarray(boxes, dtype=np.int32).reshape(-1, 4)[src])
+
+
+def page_from_llocs(llocs, strips):
+    """All text lines of a page from raw .llocs bytes: ``llocs[i]`` is the content of line i's
+    file, ``strips[i]`` its (offset_x, offset_y, height) (alignToOCR.py:153-182).
+    -> (OCR string, boxes int32[k, 4])."""
+    cps, bxs = [], []
+    for text, (off_x, off_y, height) in zip(llocs, strips):
+        c, b = _native.parse_llocs(text, off_x, off_y, off_y + height)
+        cps.append(c)
+        bxs.append(b)
+    cp = np.concatenate(cps) if cps else np.zeros(0, np.uint32)
+    boxes = np.concatenate(bxs) if bxs else np.zeros((0, 4), np.int32)
+    return cp.astype('<u4').tobytes().decode('utf-32-le', 'surrogatepass'), boxes
+
+
+def boxes_for_pages_arrays(pages, seq_align_params=None, devices=None):
+    """Many pages on arrays: ``pages`` = [(transcript str, OCR str, boxes int32[k, 4])] (the OCR
+    characters before abbreviation expansion).  One alignment launch per device, one native pass
+    over the op strings.  -> per page (syllables, syl_boxes int32[s, 4]): the syllables that got a
+    box, in order, exactly the ``CharBox`` list ``boxes_for_pages`` returns.
+
+    Pages whose transcript holds a regular-expression metacharacter or '_' take the object path
+    (the reference's regex then means something else than "first letter to last letter")."""
+    results = [None] * len(pages)
+    fast = []
+    for k, (transcript, ocr, boxes) in enumerate(pages):
+        spans = syllable_spans(transcript) if regex_free(transcript) else None
+        if spans is None:
+            chars = [CharBox(c, (int(b[0]), int(b[1])), (int(b[2]), int(b[3]))) for c, b in zip(ocr, np.asarray(boxes).reshape(-1, 4))]
+            syl_boxes = boxes_for_page(transcript, chars, seq_align_params, device=(devices or [0])[0])[0]
+            results[k] = ([b.char for b in syl_boxes],
+                          np.array([[b.ulx, b.uly, b.lrx, b.lry] for b in syl_boxes], dtype=np.int32).reshape(-1, 4))
+        else:
+            ocr2, boxes2 = expand_abbreviations_arrays(ocr, boxes)
+            fast.append((k, transcript, ocr2, np.asarray(boxes2, dtype=np.int32).reshape(-1, 4), spans))
+    if fast:
+        ops, ops_off, ops_len = tsc.align_strings([(t, o) for _, t, o, _, _ in fast], seq_align_params, devices)
+        syl_off = np.zeros(len(fast) + 1, dtype=np.int64)
+        box_off = np.zeros(len(fast) + 1, dtype=np.int64)
+        np.cumsum([f[4][1].shape[0] for f in fast], out=syl_off[1:])
+        np.cumsum([f[3].shape[0] for f in fast], out=box_off[1:])
+        out, has = _native.syllable_boxes(ops, ops_off, ops_len, np.concatenate([f[4][1] for f in fast]), syl_off,
+                                          np.concatenate([f[3] for f in fast]), box_off)
+        for j, (k, _, _, _, (syls, _)) in enumerate(fast):
+            lo, hi = int(syl_off[j]), int(syl_off[j + 1])
+            keep = has[lo:hi]
+            results[k] = ([s for s, h in zip(syls, keep.tolist()) if h], out[lo:hi][keep])
+    return results
+
+
+def to_JSON_bytes(syllables, syl_boxes, lines_peak_locs):
+    """alignToOCR.to_JSON_dict (:333-351) + json.dumps, written natively from the arrays of
+    ``boxes_for_pages_arrays``."""
+    med_line_spacing = float(np.quantile(np.diff(lines_peak_locs), 0.75))
+    if not np.isfinite(med_line_spacing):
+        return json.dumps({'median_line_spacing': med_line_spacing,
+                           'syl_boxes': [{'syl': s, 'ul': [int(b[0]), int(b[1])], 'lr': [int(b[2]), int(b[3])]}
+                                         for s, b in zip(syllables, syl_boxes)]}).encode()
+    return _native.boxes_to_json(syllables, syl_boxes, np.ones(len(syllables), np.uint8), med_line_spacing)

@@ -395,6 +395,35 @@ def perform_alignment_batch(pairs, scoring_system=None, devices=None, return_sco
     return final
 
 
+def align_strings(pairs, scoring_system=None, devices=None):
+    """(transcript str, OCR str) pairs -> (ops, ops_off, ops_len): the alignment of
+    ``perform_alignment(list(t), list(o))`` as op strings, for callers that stay on arrays
+    (alignToOCR.boxes_for_pages_arrays).  One encode for the whole batch, one launch per device."""
+    fn, match, mismatch, gox, goy, gex, gey = parse_scoring_system(scoring_system)
+    boundary = _as_int(gap_extend, 'gap_extend')
+    enc = _Encoded()
+    enc.reflexive, enc.chars = True, True
+    enc.n = np.fromiter((len(t) for t, _ in pairs), dtype=np.int32, count=len(pairs))
+    enc.m = np.fromiter((len(o) for _, o in pairs), dtype=np.int32, count=len(pairs))
+    enc.t_off, enc.o_off = _layout(enc.n, enc.m)
+    text = ''.join(t + o for t, o in pairs)
+    try:
+        if fn is not None:
+            raise UnicodeEncodeError('latin-1', '', 0, 0, 'a table needs dense codes')
+        enc.symbols = np.frombuffer(text.encode('latin-1'), dtype=np.uint8)
+        enc.alphabet = None
+    except UnicodeEncodeError:
+        cp = np.frombuffer(text.encode('utf-32-le', 'surrogatepass'), dtype=np.uint32)
+        uniq, inv = np.unique(cp, return_inverse=True)
+        dt = _code_dtype(uniq.size, fn is not None)
+        if dt is None:
+            raise ValueError('more distinct characters in one batch ({}) than the device path can code'.format(uniq.size))
+        enc.symbols = inv.astype(dt)
+        enc.alphabet = [chr(c) for c in uniq.tolist()]
+    ops, ops_off, ops_len, _ = _align_encoded(enc, fn, (match, mismatch, gox, goy, gex, gey), boundary, devices)
+    return ops, ops_off, ops_len
+
+
 def perform_alignment_sweep(pairs, scoring_systems, device=0, return_scores=False):
     """The reference's parameter sweep (evaluate_text_alignment.py:134-198 re-aligns the same
     pages under 729 scoring vectors) as ONE launch: the pairs are encoded and uploaded once and
