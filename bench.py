@@ -242,13 +242,36 @@ def crop_pairs(pairs, cells_per_pair):
     return out, whole
 
 
+_PER_CELL_S = []
+
+
+def cpu_seconds_per_cell():
+    """What one cell costs the CPU aligner on this box (one 80 x 80 alignment, measured once)."""
+    if not _PER_CELL_S:
+        fn = cpu_aligner()[0]
+        t, o = list('gloria in excelsis deo ' * 4)[:80], list('glorla ln exce1sis de0 ' * 4)[:80]
+        fn(t, o)
+        t0 = time.perf_counter()
+        fn(t, o)
+        _PER_CELL_S.append(max((time.perf_counter() - t0) / 6400.0, 1e-7) * 1.3)     # all cores busy: a bit slower
+    return _PER_CELL_S[0]
+
+
 def cpu_python_step(pairs, cores, target_s):
-    """One CPU step: the first `cores` pairs of the workload, one per host core, whole when a
-    ~10 us/cell aligner finishes them in target_s, else cropped to that budget."""
-    sample, whole = crop_pairs(pairs[:cores], target_s / 10e-6)
+    """One CPU step: the first `cores` pairs of the workload, one per host core, whole when the
+    aligner finishes them in target_s, else cropped to that budget."""
+    per_core = target_s / cpu_seconds_per_cell()
+    sample, cells, whole = [], 0, True
+    for pr in pairs:                               # as many whole pairs as the budget holds ...
+        if cells >= cores * per_core:
+            break
+        sample.append(pr)
+        cells += len(pr[0]) * len(pr[1])
+    if len(sample) <= cores:                       # ... or one (cropped, if need be) pair per core
+        sample, whole = crop_pairs(pairs[:cores], per_core)
     t0 = time.perf_counter()
     with mp.get_context('fork').Pool(cores) as pool:
-        res = pool.map(_cpu_one, sample, chunksize=1)
+        res = pool.map(_cpu_one, sample, chunksize=max(1, len(sample) // (cores * 4)))
     wall = time.perf_counter() - t0
     cells = sum(c for c, _ in res)
     return cells, wall, sample, whole
@@ -267,7 +290,7 @@ def cpu_c_oracle(packed, cores, max_pairs):
 
 
 def sample_text(sample, whole, which, kind_text):
-    return ('%d %s of %s (seeds from the head of the workload; ~%dx%d chars each), one per host core per step; %s'
+    return ('%d %s of %s (seeds from the head of the workload; ~%dx%d chars each) over the host cores per step; %s'
             % (len(sample), 'whole pairs' if whole else 'cropped pairs (first rows/columns)', which,
                len(sample[0][0]), len(sample[0][1]), kind_text))
 
@@ -278,7 +301,7 @@ def run_reference(args):
         return 0
     cores = len(os.sched_getaffinity(0))
     _, kind, kind_text = cpu_aligner()
-    _, pairs = make_workload(args.workload, 0, cores, min(cores, 16))
+    _, pairs = make_workload(args.workload, 0, cores * (512 if args.workload == 'c3' else 1), min(cores, 16))
     total = args.steps + args.warmup
     # whole run within a few minutes: ~240 s of CPU steps, a c2 page is ~21 s on one core
     target_s = max(0.5, min(30.0, 240.0 / max(total, 1)))

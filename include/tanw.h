@@ -136,10 +136,12 @@ int  tanw_set_long_band_rows(tanw_ctx *ctx, int rows);
  * per pair, general recurrences); a pair whose pointers exceed one warp's share of the arena takes
  * the chained-stripe path and its row bands like any other. */
 int  tanw_set_symbol_bytes(tanw_ctx *ctx, int bytes);
-/* Pairs with m <= 128 and n <= 4096 are aligned four per warp by the line kernel (8 lanes per
- * pair; BASELINE config 3).  enabled = 0 sends them through the page kernel instead (same
- * results; used by the tests to compare the two paths).  Default: enabled. */
-int  tanw_set_line_kernel(tanw_ctx *ctx, int enabled);
+/* Pairs with m <= 128 and n <= 4096 are aligned by the line kernels (8 lanes per pair; BASELINE
+ * config 3): eight per warp, two per 32-bit register, when their scores fit 16 bits (gap opens
+ * <= 0, equality scorer with match >= mismatch, (2n + 132) * max|param| <= 8000), else four per
+ * warp in int32.  mode 0 sends them through the page kernel instead, 2 through the int32 line
+ * kernel only (same results on every route; used by the tests to compare them).  Default: 1. */
+int  tanw_set_line_kernel(tanw_ctx *ctx, int mode);
 
 /* ---- one-call batch alignment: the entry the reference's call site maps to ------------------
  * Replaces N calls of textSeqCompare.perform_alignment (textSeqCompare.py:13) -- copies the

@@ -720,3 +720,75 @@ def test_wide_symbol_pair_beyond_the_arena_is_banded(oracle):
     finally:
         ctx.close()
     _ = oracle
+
+
+def _same_results(a, b, count):
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    for k in range(count):
+        assert np.array_equal(a[0][a[1][k]:a[1][k] + a[2][k]], b[0][b[1][k]:b[1][k] + b[2][k]]), k
+
+
+def test_line16_kernel_matches_int32_line_kernel_and_oracle(oracle):
+    """The .u16x2 line kernel (two pairs per register, eight per warp) against the int32 line
+    kernel on the same batch and against the oracle: strip-width class edges, octets padded with
+    empty slots, cell-less pairs, heights either side of the 16-bit range limit (taller pairs
+    stay on the int32 kernel), gap_extend_y != 0 (variant 1), and scoring systems that are not
+    eligible at all (general recurrences, mismatch > match)."""
+    from text_alignment_b200 import _native
+    sizes = [(1, 1), (1, 128), (128, 1), (7, 32), (8, 33), (9, 64), (40, 65), (41, 96), (120, 97), (119, 128),
+             (334, 90), (335, 90), (333, 128), (400, 60), (2, 2), (0, 7), (7, 0), (0, 0), (64, 64), (63, 64), (65, 64)]
+    pairs = [synth.make_pair(90 + k, n, m, 1, 6) if n and m else ('a' * n, 'b' * m) for k, (n, m) in enumerate(sizes)]
+    pairs += [synth.c3_pair(70000 + k) for k in range(3000)]
+    random.Random(4).shuffle(pairs)
+    buf, t_off, n, o_off, m = _pack(pairs)
+    ctx = _native.Context(0)
+    try:
+        for params in (DEFAULT, (7, -3, -4, -9, -1, -2, -1), (5, -4, -2, -7, 0, -5, -3), (11, -10, -7, -7, -5, -5, -1),
+                       (7, 2, 3, -4, -1, 1, 0), (-4, 8, -7, -7, -3, 0, -1)):
+            sc = ctx.make_scoring(*params)
+            ctx.set_line_kernel(1)
+            a = ctx.align_batch(buf, t_off, n, o_off, m, sc)
+            launches = ctx.timing()['kernel_launches']
+            ctx.set_line_kernel(2)
+            b = ctx.align_batch(buf, t_off, n, o_off, m, sc)
+            _same_results(a, b, len(pairs))
+            eligible = params[2] <= 0 and params[3] <= 0 and params[0] >= params[1]
+            # 16-bit fill + traceback kernels (if eligible) + int32 line kernel (the tall pairs) 
+            assert (launches >= 2) if eligible else (launches <= 2), (params, launches)
+            osc, _ = oracle.make_scoring(list(params[:6]), boundary_gap=params[6])
+            r_ops, r_off, r_len, r_end = oracle.align_batch_codes(buf, t_off, n, o_off, m, osc, threads=8)
+            assert a[2].tolist() == r_len.tolist()
+            for k in range(len(pairs)):
+                assert np.array_equal(a[0][a[1][k]:a[1][k] + a[2][k]], r_ops[r_off[k]:r_off[k] + r_len[k]]), (params, k)
+                got = tuple(None if v == -1073741824 else int(v) for v in a[3][k].tolist())
+                assert got == _end(r_end[k].tolist()), (params, k, n[k], m[k])
+        # incomplete octets
+        for count in (1, 2, 3, 5, 9, 17):
+            sub = _pack(pairs[:count])
+            ctx.set_line_kernel(1)
+            a = ctx.align_batch(*sub, ctx.make_scoring(*DEFAULT))
+            ctx.set_line_kernel(0)
+            b = ctx.align_batch(*sub, ctx.make_scoring(*DEFAULT))
+            _same_results(a, b, count)
+    finally:
+        ctx.close()
+
+
+def test_line16_rescore_needs_an_eligible_system():
+    from text_alignment_b200 import _native
+    pairs = [synth.c3_pair(k) for k in range(64)]
+    ctx = _native.Context(0)
+    try:
+        ctx.prepare(*_pack(pairs), ctx.make_scoring(*DEFAULT))
+        ctx.run()
+        a = ctx.fetch()
+        ctx.rescore(ctx.make_scoring(5, -4, -2, -7, 0, -5, -1))        # still eligible
+        ctx.run()
+        ctx.fetch()
+        with pytest.raises(_native.NativeError):                     # a positive gap open: prepare again
+            ctx.rescore(ctx.make_scoring(7, 2, 3, -4, -1, 1, 0))
+        ctx.rescore(ctx.make_scoring(*DEFAULT))
+        ctx.run()
+        _same_results(a, ctx.fetch(), len(pairs))
+    finally:
+        ctx.close()

@@ -84,15 +84,20 @@ class NativeError(RuntimeError):
     pass
 
 
-def load():
-    """Load libtanw.so (built in-tree by __graft_entry__.build()); fail loudly if absent."""
+def load(path=None):
+    """Load libtanw.so (built in-tree by __graft_entry__.build()); fail loudly if absent.
+    `path`: another build of the library (tools/: kernel variants, the TANW_CHECKED build); it must
+    be given before anything else has loaded the library."""
     global _lib
     with _lib_lock:
+        if _lib is not None and path is not None and os.path.abspath(path) != _lib._name:
+            raise NativeError('libtanw is already loaded from %s' % _lib._name)
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
+            path = os.path.abspath(path) if path else LIB_PATH
+            if not os.path.exists(path):
                 raise NativeError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
-                                  '(there is no CPU fallback)' % LIB_PATH)
-            lib = ctypes.CDLL(LIB_PATH)
+                                  '(there is no CPU fallback)' % path)
+            lib = ctypes.CDLL(path)
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)      # AttributeError if the symbol is missing
                 fn.restype = res
@@ -267,9 +272,11 @@ class Context(object):
             self._check(self._lib.tanw_set_symbol_bytes(self._h, width))
             self._sym_bytes = width
 
-    def set_line_kernel(self, enabled):
-        """Route short pairs (m <= 128) through the four-pairs-per-warp kernel (default on)."""
-        self._check(self._lib.tanw_set_line_kernel(self._h, 1 if enabled else 0))
+    def set_line_kernel(self, mode):
+        """Route of short pairs (m <= 128): 1 / True = the line kernels (two pairs per register when
+        the scores fit 16 bits, else four pairs per warp in int32; default), 2 = the int32 line
+        kernel only, 0 / False = the page kernel."""
+        self._check(self._lib.tanw_set_line_kernel(self._h, int(mode)))
 
     @staticmethod
     def _canon(symbols, t_off, n, o_off, m):

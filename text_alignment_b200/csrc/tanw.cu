@@ -9,6 +9,10 @@
 //   s_k    the table kernels (tanw_tables.cuh: everything the align kernels need is derived from
 //          the pair arrays on the device; the host only waits for a 1 KB survey of the batch to
 //          size its scratch), then the align kernels, chunk after chunk;
+//   s_k2   the page kernel of a chunk, beside the chunk's line kernels on s_k (disjoint parts of the
+//          pointer arena): a batch of lines always has a few pairs that are pages, and their kernel
+//          -- one warp per pair, ~50 us however few they are -- fills the tail of the line kernel
+//          instead of following it;
 //   s_out  device -> host copies of a chunk's op strings / lengths / scores while the next
 //          chunk is being aligned.
 // tanw_align_batch cuts a batch whose copies matter (10^5 short line pairs: 40 MB of copies for
@@ -16,6 +20,7 @@
 // (prepare / run / fetch) treats the batch as one chunk.
 #include "tanw.h"
 #include "tanw_launch.h"
+#include "tanw_lines16.cuh"
 #include "tanw_tables.cuh"
 
 #include <algorithm>
@@ -81,9 +86,11 @@ struct ChunkPlan {
     int64_t ops_base = 0, cap = 0;                  // its bytes of the canonical op layout
     int64_t cells = 0;
     int n_page = 0, n_line = 0, n_quads = 0;
-    int line_class[4] = {0, 0, 0, 0};
+    int n_line16 = 0, n_octets = 0;                 // pairs / warps' work units of the 16-bit line kernel
+    int line_class[4] = {0, 0, 0, 0}, line16_class[4] = {0, 0, 0, 0};
     int page_shift = 0;                             // quantisation of n*m for the page order keys
     int piece = 0;                                  // symbol piece that completes the chunk's inputs
+    bool tables_built = false;
 };
 
 struct LongPair {
@@ -98,10 +105,10 @@ struct LongPair {
 struct tanw_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr;
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr,
                 ev_d2h0 = nullptr, ev_d2h1 = nullptr, ev_tab = nullptr, ev_survey = nullptr, ev_idle = nullptr;
-    cudaEvent_t ev_piece[kPieces] = {}, ev_chunk[kMaxChunks] = {};
+    cudaEvent_t ev_piece[kPieces] = {}, ev_chunk[kMaxChunks] = {}, ev_fork[kMaxChunks] = {}, ev_pages[kMaxChunks] = {};
     std::string err;
     int64_t arena_limit = 0;
     int64_t max_nm = 0;                   // largest n+m of the prepared batch (range check on rescore)
@@ -116,7 +123,8 @@ struct tanw_ctx {
     size_t h_subst_cap = 0;
     KParams *h_kparams = nullptr;         // pinned: per-pair scoring systems of a multi batch
     size_t h_kparams_cap = 0;
-    bool use_lines = true;
+    int line_mode = 1;                    // 0: no line kernels, 1: both, 2: the int32 line kernel only
+    int line16_max_n = 0;                 // tallest pair of the prepared batch on the 16-bit line kernel (0: none)
     int long_capacity = 0;                // resident warps for a cooperative launch
     int long_epoch = 0;                   // stamps the chain records of a launch
     int long_band_rows = 0;               // 0 = one band unless the pointer block exceeds the arena limit
@@ -137,9 +145,11 @@ struct tanw_ctx {
     int var = 0;                          // recurrence variant of the batch (tanw_kernels.cuh)
     BatchArgs args;
     LineArgs largs;
-    int64_t slot_bytes = 0, line_slot = 0;
-    int grid = 0, line_grid = 0;
-    int occ_plain = 0, occ_subst = 0, occ_line = 0;
+    TableArgs ta;                         // the table kernels' arguments of the prepared batch
+    int table_launches = 0;
+    int64_t slot_bytes = 0, line_slot = 0, line16_slot = 0;
+    int grid = 0, line_grid = 0, line16_grid = 0;
+    int occ_plain = 0, occ_subst = 0, occ_line = 0, occ_line16 = 0;
     tanw_timing timing;
 };
 
@@ -216,6 +226,16 @@ int variant_of(const tanw_scoring *sc)
 {
     if (!(sc->gap_open_x <= 0 && sc->gap_open_y <= 0)) return 0;
     return sc->gap_extend_y == 0 ? 2 : 1;
+}
+
+// Tallest line pair the 16-bit line kernel may take under a scoring system (tanw_lines16.cuh): the
+// D-only recurrences (gap opens <= 0), an equality scorer with match >= mismatch, and every value a
+// half can hold -- (2n + m + 4) * max|param| with m <= 128 -- within kRange16.  0: not eligible.
+int line16_limit(const tanw_scoring *sc)
+{
+    if (sc->subst || variant_of(sc) < 1 || sc->match < sc->mismatch) return 0;
+    const int64_t n = (kRange16 / scoring_pmax(sc) - (kLineMaxM + 4)) / 2;
+    return (int)std::max<int64_t>(0, std::min<int64_t>(n, kLineMaxN));
 }
 
 // The table of a tabulated scorer in kernel encoding, uploaded from a pinned copy the context
@@ -355,6 +375,25 @@ int run_long_pair(tanw_ctx *ctx, const LongPair &lp, const KParams &kp_pair, int
     return TANW_OK;
 }
 
+// Pair descriptors, routes and work orders of one chunk (tanw_tables.cuh), on the compute stream.
+int build_chunk_tables(tanw_ctx *ctx, int c)
+{
+    ChunkPlan &cp = ctx->chunk[c];
+    if (cp.tables_built || cp.count <= 0) return TANW_OK;
+    const TableArgs &ta = ctx->ta;
+    TANW_CUDA(ctx, cudaMemsetAsync((int *)ctx->d_hist.p + (size_t)c * kHistStride, 0, sizeof(int) * kHistStride, ctx->s_k));
+    const unsigned tiles = (unsigned)((cp.count + kTile - 1) / kTile);
+    build_kernel<<<tiles, kTileThreads, 0, ctx->s_k>>>(ta, c, cp.page_shift);
+    bins_kernel<<<1, 1024, 0, ctx->s_k>>>(ta, c, make_int4(cp.line16_class[0], cp.line16_class[1], cp.line16_class[2], cp.line16_class[3]),
+                                          make_int4(cp.line_class[0], cp.line_class[1], cp.line_class[2], cp.line_class[3]));
+    scatter_kernel<<<(unsigned)((cp.count + kTileThreads - 1) / kTileThreads), kTileThreads, 0, ctx->s_k>>>(ta, c, cp.page_shift);
+    TANW_CUDA(ctx, cudaGetLastError());
+    ctx->table_launches += 3;
+    ctx->timing.table_launches = ctx->table_launches;
+    cp.tables_built = true;
+    return TANW_OK;
+}
+
 // ops_off is canonical when pair p's bytes start where pair p-1's capacity (n+m) ends.
 bool layout_is_canonical(const int64_t *ops_off, const int32_t *n, const int32_t *m, int64_t P)
 {
@@ -457,7 +496,8 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ta.chunk_pairs = slice_pairs;
     ta.long_cells = ctx->long_cells;
     ta.slot_limit = limit;
-    ta.use_lines = (ctx->use_lines && !multi) ? 1 : 0;
+    ta.use_lines = (ctx->line_mode != 0 && !multi) ? 1 : 0;
+    ta.line16_max_n = (ctx->line_mode == 1 && !multi && sb == 1) ? line16_limit(sc) : 0;
     ta.wide = sb == 2 ? 1 : 0;
     ta.tiny_batch = P <= 2 ? 1 : 0;
     ta.can_long = ctx->long_capacity > 0 ? 1 : 0;
@@ -538,14 +578,16 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
 
     // ---- chunks: merge the survey's slices ----------------------------------------------------------
     const int n_slices = (int)std::max<int64_t>((P + slice_pairs - 1) / slice_pairs, 1);
-    int64_t cells = 0, page_cells = 0, cap_total = 0, max_slot = 0, max_line_slot = 0;
-    int max_n = 0, n_page_total = 0, n_line_total = 0;
+    int64_t cells = 0, page_cells = 0, cap_total = 0, max_slot = 0, max_line_slot = 0, max_line16_slot = 0;
+    int max_n = 0, n_page_total = 0, n_line_total = 0, max_nm16 = 0;
     for (int s = 0; s < n_slices; ++s) {
         const ChunkSurvey &cs = sv.chunk[s];
         cells += cs.cells; page_cells += cs.page_cells; cap_total += cs.cap;
         max_slot = std::max<int64_t>(max_slot, cs.max_slot);
         max_line_slot = std::max<int64_t>(max_line_slot, cs.max_line_slot);
+        max_line16_slot = std::max<int64_t>(max_line16_slot, cs.max_line16_slot);
         max_n = std::max(max_n, cs.max_n_page);
+        max_nm16 = std::max(max_nm16, cs.max_n_line16);
         n_page_total += cs.n_page; n_line_total += cs.n_line;
     }
     int S = 1;
@@ -563,7 +605,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     S = (n_slices + per - 1) / per;
     ctx->n_chunks = S;
     int64_t ops_base = 0;
-    int max_quads = 0, max_page = 0;
+    int max_quads = 0, max_octets = 0, max_page = 0, n_line16_total = 0;
     for (int c = 0; c < S; ++c) {
         ChunkPlan &cp = ctx->chunk[c];
         cp = ChunkPlan();
@@ -574,16 +616,18 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         for (int s = c * per; s < std::min(n_slices, (c + 1) * per); ++s) {
             const ChunkSurvey &cs = sv.chunk[s];
             cp.cap += cs.cap; cp.cells += cs.cells;
-            cp.n_page += cs.n_page; cp.n_line += cs.n_line;
-            for (int k = 0; k < 4; ++k) cp.line_class[k] += cs.line_class[k];
+            cp.n_page += cs.n_page; cp.n_line += cs.n_line; cp.n_line16 += cs.n_line16;
+            for (int k = 0; k < 4; ++k) { cp.line_class[k] += cs.line_class[k]; cp.line16_class[k] += cs.line16_class[k]; }
             max_pc = std::max<int64_t>(max_pc, cs.max_page_cells);
             sym_end = std::max<int64_t>(sym_end, cs.sym_end);
         }
-        for (int k = 0; k < 4; ++k) cp.n_quads += (cp.line_class[k] + 3) / 4;
+        for (int k = 0; k < 4; ++k) { cp.n_quads += (cp.line_class[k] + 3) / 4; cp.n_octets += (cp.line16_class[k] + 7) / 8; }
         while ((max_pc >> cp.page_shift) >= kPageKeys) ++cp.page_shift;
         cp.piece = (int)std::min<int64_t>(kPieces - 1, std::max<int64_t>(sym_end * sb - 1, 0) / piece_bytes);
         ops_base += cp.cap;
         max_quads = std::max(max_quads, cp.n_quads);
+        max_octets = std::max(max_octets, cp.n_octets);
+        n_line16_total += cp.n_line16;
         max_page = std::max(max_page, cp.n_page);
     }
     const int64_t chunk_pairs = (int64_t)per * slice_pairs;
@@ -619,7 +663,15 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     const int64_t line_slot = (max_line_slot + 255) / 256 * 256;
     ctx->line_grid = line_grid;
     ctx->line_slot = line_slot;
-    const int64_t line_arena = max_quads ? (int64_t)line_grid * kWarpsPerBlock * 4 * line_slot : 0;
+    int64_t line_arena = max_quads ? (int64_t)line_grid * kWarpsPerBlock * 4 * line_slot : 0;
+    int line16_grid = ctx->sm_count * ctx->occ_line16;
+    if (((int64_t)max_octets + kWarpsPerBlock - 1) / kWarpsPerBlock < line16_grid)
+        line16_grid = (int)std::max<int64_t>(((int64_t)max_octets + kWarpsPerBlock - 1) / kWarpsPerBlock, 1);
+    const int64_t line16_slot = (max_line16_slot + 255) / 256 * 256;
+    ctx->line16_grid = line16_grid;
+    ctx->line16_slot = line16_slot;
+    ctx->line16_max_n = n_line16_total > 0 ? std::max(max_nm16, 1) : 0;     // the tallest pair routed to the 16-bit kernel
+    if (max_octets) line_arena = std::max(line_arena, (int64_t)line16_grid * kWarpsPerBlock * 8 * line16_slot);
     const int bnd_rows = max_n + 4;      // bnd[1..n] plus the prefetch overrun
 
     if (ctx->d_pairs.reserve(sizeof(PairDesc) * Pz) != cudaSuccess ||
@@ -627,9 +679,9 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         ctx->d_order.reserve(sizeof(int) * Pz) != cudaSuccess ||
         ctx->d_lsorted.reserve(sizeof(int) * Pz) != cudaSuccess ||
         ctx->d_hist.reserve(sizeof(int) * (size_t)kHistStride * (size_t)S) != cudaSuccess ||
-        ctx->d_classes.reserve(sizeof(LineClasses) * kMaxChunks) != cudaSuccess ||
-        ctx->d_counter.reserve(sizeof(unsigned) * 2 * kMaxChunks) != cudaSuccess ||
-        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(std::max(slots * slot_bytes, max_long), line_arena), 256)) != cudaSuccess ||
+        ctx->d_classes.reserve(sizeof(LineClasses) * 2 * kMaxChunks) != cudaSuccess ||
+        ctx->d_counter.reserve(sizeof(unsigned) * 4 * kMaxChunks) != cudaSuccess ||
+        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(slots * slot_bytes + line_arena, max_long), 256)) != cudaSuccess ||
         ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(slots * bnd_rows, 1)) != cudaSuccess ||
         reserve_zeroed(ctx, ctx->d_chain, sizeof(int4) * (size_t)max_long_bnd) != cudaSuccess ||
         ctx->d_ck.reserve(sizeof(int) * (size_t)(4 + max_ck)) != cudaSuccess ||
@@ -680,7 +732,9 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
             return fail(ctx, TANW_E_INVALID, "symbol code %d >= subst_k %d", ctx->h_misc[1], sc->subst_k);
     }
 
-    // ---- the tables, chunk by chunk, on the device --------------------------------------------------
+    // ---- the tables, chunk by chunk, on the device: now for the three-phase form; a pipelined batch
+    // builds a chunk's tables right before its align kernels (run_impl), so that the first chunk's
+    // alignment does not wait for the tables of the others --------------------------------------------
     ta.chunk_pairs = chunk_pairs;
     ta.pairs = (PairDesc *)ctx->d_pairs.p;
     ta.route = (unsigned char *)ctx->d_route.p;
@@ -688,18 +742,12 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ta.line_sorted = (int *)ctx->d_lsorted.p;
     ta.hist = (int *)ctx->d_hist.p;
     ta.classes = (LineClasses *)ctx->d_classes.p;
-    int table_launches = n_tiles > 0 ? 1 : 0;
-    for (int c = 0; c < S && P > 0; ++c) {
-        const ChunkPlan &cp = ctx->chunk[c];
-        if (cp.count <= 0) continue;
-        TANW_CUDA(ctx, cudaMemsetAsync((int *)ctx->d_hist.p + (size_t)c * kHistStride, 0, sizeof(int) * kHistStride, ctx->s_k));
-        const unsigned tiles = (unsigned)((cp.count + kTile - 1) / kTile);
-        build_kernel<<<tiles, kTileThreads, 0, ctx->s_k>>>(ta, c, cp.page_shift);
-        bins_kernel<<<1, 1024, 0, ctx->s_k>>>(ta, c, make_int4(cp.line_class[0], cp.line_class[1], cp.line_class[2], cp.line_class[3]));
-        scatter_kernel<<<(unsigned)((cp.count + kTileThreads - 1) / kTileThreads), kTileThreads, 0, ctx->s_k>>>(ta, c, cp.page_shift);
-        TANW_CUDA(ctx, cudaGetLastError());
-        table_launches += 3;
-    }
+    ctx->ta = ta;
+    ctx->table_launches = n_tiles > 0 ? 1 : 0;
+    for (int c = 0; c < S; ++c) ctx->chunk[c].tables_built = false;
+    if (!in.pipelined)
+        for (int c = 0; c < S; ++c)
+            if (int rc = build_chunk_tables(ctx, c)) return rc;
 
     BatchArgs &a = ctx->args;
     memset(&a, 0, sizeof a);
@@ -720,7 +768,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     memset(&la, 0, sizeof la);
     la.sym = a.sym;
     la.pairs = a.pairs;
-    la.ptr_arena = a.ptr_arena;
+    la.ptr_arena = a.ptr_arena + (size_t)(slots * slot_bytes);        // behind the page kernel's slots
     la.slot_bytes = line_slot;
     la.ops = a.ops;
     la.ops_len = a.ops_len;
@@ -733,7 +781,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->timing.ptr_bytes = cells;
     ctx->timing.h2d_bytes = h2d;
     ctx->timing.chunks = S;
-    ctx->timing.table_launches = table_launches;
+    ctx->timing.table_launches = ctx->table_launches;
     ctx->timing.host_prepare_ms = host_timer.ms();
     ctx->prepared = true;
     return TANW_OK;
@@ -747,16 +795,31 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
     if (!pipelined || ctx->multi || ctx->use_subst) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_h2d1, 0));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->s_k));
     int launches = 0;
-    TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned) * 2 * kMaxChunks, ctx->s_k));
+    TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned) * 4 * kMaxChunks, ctx->s_k));
     TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_misc.p, 0, sizeof(int), ctx->s_k));
+    bool cp_forked[kMaxChunks] = {};
     for (int c = 0; c < ctx->n_chunks; ++c) {
+        if (int rc = build_chunk_tables(ctx, c)) return rc;
         const ChunkPlan &cp = ctx->chunk[c];
         if (pipelined) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_piece[cp.piece], 0));
+        const bool forked = cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0);
+        if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_fork[c], ctx->s_k));
+        if (cp.n_octets > 0) {
+            LineArgs la = ctx->largs;
+            la.sorted = (const int *)ctx->d_lsorted.p + cp.first;
+            la.classes = (const LineClasses *)ctx->d_classes.p + 2 * c;
+            la.counter = (unsigned *)ctx->d_counter.p + 4 * c + 2;
+            la.slot_bytes = ctx->line16_slot;
+            la.n_quads = cp.n_octets;
+            const int grid = (int)std::min<int64_t>(ctx->line16_grid, ((int64_t)cp.n_octets + kWarpsPerBlock - 1) / kWarpsPerBlock);
+            TANW_CUDA(ctx, launch_lines16(la, ctx->kp, ctx->var, std::max(grid, 1), ctx->s_k));
+            ++launches;
+        }
         if (cp.n_quads > 0) {
             LineArgs la = ctx->largs;
             la.sorted = (const int *)ctx->d_lsorted.p + cp.first;
-            la.classes = (const LineClasses *)ctx->d_classes.p + c;
-            la.counter = (unsigned *)ctx->d_counter.p + 2 * c + 1;
+            la.classes = (const LineClasses *)ctx->d_classes.p + 2 * c + 1;
+            la.counter = (unsigned *)ctx->d_counter.p + 4 * c + 1;
             la.n_quads = cp.n_quads;
             const int grid = (int)std::min<int64_t>(ctx->line_grid, ((int64_t)cp.n_quads + kWarpsPerBlock - 1) / kWarpsPerBlock);
             TANW_CUDA(ctx, launch_lines(la, ctx->kp, ctx->var, ctx->use_subst, std::max(grid, 1), ctx->s_k));
@@ -765,14 +828,22 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
         if (cp.n_page > 0) {
             BatchArgs a = ctx->args;
             a.order = (const int *)ctx->d_order.p + cp.first;
-            a.counter = (unsigned *)ctx->d_counter.p + 2 * c;
+            a.counter = (unsigned *)ctx->d_counter.p + 4 * c;
             a.n_pairs = cp.n_page;
             const int grid = (int)std::min<int64_t>(ctx->grid, ((int64_t)cp.n_page + kWarpsPerBlock - 1) / kWarpsPerBlock);
+            cudaStream_t st = forked ? ctx->s_k2 : ctx->s_k;
+            if (forked) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k2, ctx->ev_fork[c], 0));
             TANW_CUDA(ctx, launch_pairs(a, ctx->kp, ctx->var, ctx->use_subst, ctx->batch_sym_bytes, ctx->multi,
-                                        std::max(grid, 1), ctx->s_k));
+                                        std::max(grid, 1), st));
+            if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_pages[c], ctx->s_k2));
             ++launches;
         }
+        cp_forked[c] = forked;
         if (c + 1 == ctx->n_chunks) {
+            // join the page kernels before anything else touches the arena, and so that the
+            // stream the caller sees (tanw_stream_handle) covers all of the batch's work
+            for (int j = 0; j <= c; ++j)
+                if (cp_forked[j]) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_pages[j], 0));
             for (const LongPair &lp : ctx->longs) {
                 const KParams kp = ctx->multi ? ctx->h_kparams[lp.sidx] : ctx->kp;
                 int rc = run_long_pair(ctx, lp, kp, ctx->var, &launches);
@@ -820,6 +891,8 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
     for (int c = 0; c < ctx->n_chunks; ++c) {
         const ChunkPlan &cp = ctx->chunk[c];
         TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_chunk[c], 0));
+        if (cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0))
+            TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_pages[c], 0));
         if (c == 0) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h0, ctx->s_out));
         if (cp.cap > 0) {
             TANW_CUDA(ctx, cudaMemcpyAsync(dst + cp.ops_base, (const uint8_t *)ctx->d_ops.p + cp.ops_base, (size_t)cp.cap,
@@ -941,7 +1014,7 @@ int tanw_create(int device, tanw_ctx **out)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     DeviceGuard guard(device);
     cudaError_t e = guard.err;
-    cudaStream_t *streams[] = { &ctx->s_in, &ctx->s_k, &ctx->s_out };
+    cudaStream_t *streams[] = { &ctx->s_in, &ctx->s_k, &ctx->s_k2, &ctx->s_out };
     for (auto s : streams)
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = { &ctx->ev_h2d0, &ctx->ev_h2d1, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_d2h0, &ctx->ev_d2h1 };
@@ -952,8 +1025,11 @@ int tanw_create(int device, tanw_ctx **out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     for (int i = 0; i < kPieces; ++i)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_piece[i], cudaEventDisableTiming);
-    for (int i = 0; i < kMaxChunks; ++i)
+    for (int i = 0; i < kMaxChunks; ++i) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pages[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_survey, sizeof(Survey));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_misc, 256);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_idle, ctx->s_k);
@@ -967,6 +1043,7 @@ int tanw_create(int device, tanw_ctx **out)
     ctx->occ_plain = std::max(1, pairs_blocks_per_sm(false));
     ctx->occ_subst = std::max(1, pairs_blocks_per_sm(true));
     ctx->occ_line = std::max(1, lines_blocks_per_sm());
+    ctx->occ_line16 = std::max(1, lines16_blocks_per_sm());
     {
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
@@ -981,7 +1058,7 @@ int tanw_destroy(tanw_ctx *ctx)
 {
     if (!ctx) return TANW_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t streams[] = { ctx->s_in, ctx->s_k, ctx->s_out };
+    cudaStream_t streams[] = { ctx->s_in, ctx->s_k, ctx->s_k2, ctx->s_out };
     for (auto s : streams)
         if (s) cudaStreamSynchronize(s);
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_n, &ctx->d_m, &ctx->d_toff, &ctx->d_ooff, &ctx->d_pairs, &ctx->d_route,
@@ -996,6 +1073,10 @@ int tanw_destroy(tanw_ctx *ctx)
     for (auto ev : ctx->ev_piece)
         if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_chunk)
+        if (ev) cudaEventDestroy(ev);
+    for (auto ev : ctx->ev_fork)
+        if (ev) cudaEventDestroy(ev);
+    for (auto ev : ctx->ev_pages)
         if (ev) cudaEventDestroy(ev);
     if (ctx->h_survey) cudaFreeHost(ctx->h_survey);
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
@@ -1044,10 +1125,11 @@ int tanw_set_long_band_rows(tanw_ctx *ctx, int rows)
     return TANW_OK;
 }
 
-int tanw_set_line_kernel(tanw_ctx *ctx, int enabled)
+int tanw_set_line_kernel(tanw_ctx *ctx, int mode)
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
-    ctx->use_lines = enabled != 0;
+    if (mode < 0 || mode > 2) return fail(ctx, TANW_E_INVALID, "line kernel mode must be 0, 1 or 2");
+    ctx->line_mode = mode;
     ctx->prepared = false;
     return TANW_OK;
 }
@@ -1065,6 +1147,7 @@ int tanw_sync(tanw_ctx *ctx)
     TANW_ENTER(ctx);
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
+    TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k2));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return TANW_OK;
 }
@@ -1100,6 +1183,9 @@ int tanw_batch_rescore(tanw_ctx *ctx, const tanw_scoring *sc)
     if (sc->subst && sc->subst_k != ctx->kp.subst_k)
         return fail(ctx, TANW_E_INVALID, "rescore needs a table of the same size (K = %d)", ctx->kp.subst_k);
     if (!in_range(scoring_pmax(sc), ctx->max_nm)) return fail(ctx, TANW_E_RANGE, "%s", kRangeMessage);
+    if (ctx->line16_max_n > line16_limit(sc))
+        return fail(ctx, TANW_E_STATE, "this scoring system cannot use the 16-bit line kernel the batch was routed to "
+                    "(gap opens <= 0, match >= mismatch, small scores): prepare the batch again");
     TANW_ENTER(ctx);
     const KParams old = ctx->kp;
     ctx->kp = make_kparams(sc);
@@ -1191,7 +1277,7 @@ int tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s)
     if (which < 0 || which > 3) return fail(ctx, TANW_E_INVALID, "which must be 0, 1, 2 or 3");
     TANW_ENTER(ctx);
     ctx->prepared = ctx->ran = false;                     // borrows the score / counter buffers of the batch
-    if (ctx->d_counter.reserve(sizeof(unsigned) * 2 * kMaxChunks + 256) != cudaSuccess ||
+    if (ctx->d_counter.reserve(sizeof(unsigned) * 4 * kMaxChunks + 256) != cudaSuccess ||
         ctx->d_scores.reserve(4096 * sizeof(int)) != cudaSuccess)
         return fail(ctx, TANW_E_NOMEM, "device allocation failed");
     const int iters = 1 << 13, blocks = ctx->sm_count * 8, threads = 256;
@@ -1207,7 +1293,7 @@ int tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s)
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         TANW_CUDA(ctx, cudaEventRecord(e0, ctx->s_k));
-        int *sink = (int *)ctx->d_counter.p + 2 * kMaxChunks;
+        int *sink = (int *)ctx->d_counter.p + 4 * kMaxChunks;
         if (which == 0)      int32_peak_kernel<0><<<blocks, threads, 0, ctx->s_k>>>(iters, src, sink, 3, 5);
         else if (which == 1) int32_peak_kernel<1><<<blocks, threads, 0, ctx->s_k>>>(iters, src, sink, 3, 5);
         else if (which == 2) int32_peak_kernel<2><<<blocks, threads, 0, ctx->s_k>>>(iters, src, sink, 3, 5);

@@ -217,22 +217,29 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
     y_out = EYZ ? ypl : ypl - kp.ey;
 }
 
-template <int C>
+// STREAM: evict-first stores (a page's pointers are 2-3 MB that nothing reads before the pair's
+// traceback, 22 GB per launch of config 2); the line kernels read a pair's few KB back within
+// microseconds and store with the default policy so that they are still in L2 then.
+template <int C, bool STREAM = true>
 __device__ __forceinline__ void store_ptr_words(uint8_t *dst, const unsigned (&pw)[C / 4])
 {
     if (C % 16 == 0) {
 #pragma unroll
-        for (int v = 0; v < C / 16; ++v)
-            __stcs(reinterpret_cast<uint4 *>(dst) + v,
-                   make_uint4(pw[4 * v], pw[4 * v + 1], pw[4 * v + 2], pw[4 * v + 3]));
+        for (int v = 0; v < C / 16; ++v) {
+            const uint4 q = make_uint4(pw[4 * v], pw[4 * v + 1], pw[4 * v + 2], pw[4 * v + 3]);
+            if (STREAM) __stcs(reinterpret_cast<uint4 *>(dst) + v, q); else __stcg(reinterpret_cast<uint4 *>(dst) + v, q);
+        }
     } else if (C % 8 == 0) {
 #pragma unroll
-        for (int v = 0; v < C / 8; ++v)
-            __stcs(reinterpret_cast<uint2 *>(dst) + v, make_uint2(pw[2 * v], pw[2 * v + 1]));
+        for (int v = 0; v < C / 8; ++v) {
+            const uint2 q = make_uint2(pw[2 * v], pw[2 * v + 1]);
+            if (STREAM) __stcs(reinterpret_cast<uint2 *>(dst) + v, q); else __stcg(reinterpret_cast<uint2 *>(dst) + v, q);
+        }
     } else {
 #pragma unroll
-        for (int v = 0; v < C / 4; ++v)
-            __stcs(reinterpret_cast<unsigned *>(dst) + v, pw[v]);
+        for (int v = 0; v < C / 4; ++v) {
+            if (STREAM) __stcs(reinterpret_cast<unsigned *>(dst) + v, pw[v]); else __stcg(reinterpret_cast<unsigned *>(dst) + v, pw[v]);
+        }
     }
 }
 
@@ -884,8 +891,8 @@ struct LineArgs {
     const int      *sorted;      // the chunk's line pairs, sorted
     const LineClasses *classes;
     unsigned       *counter;
-    int             n_quads;
-    uint8_t        *ptr_arena;   // slot_bytes per 8-lane group
+    int             n_quads;     // work units of this launch (quads; octets of the 16-bit kernel)
+    uint8_t        *ptr_arena;   // slot_bytes per 8-lane group (16-bit kernel: per pair of a group)
     long long       slot_bytes;
     uint8_t        *ops;
     int            *ops_len;

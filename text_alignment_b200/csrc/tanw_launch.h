@@ -16,6 +16,9 @@ int pairs_blocks_per_sm(bool subst);
 
 cudaError_t launch_lines(const LineArgs &a, const KParams &kp, int var, bool subst, int grid, cudaStream_t stream);
 int lines_blocks_per_sm();
+// the .u16x2 line kernel (tanw_lines16.cuh): var 1 or 2, equality scorer, match >= mismatch
+cudaError_t launch_lines16(const LineArgs &a, const KParams &kp, int var, int grid, cudaStream_t stream);
+int lines16_blocks_per_sm();
 
 const void *long_kernel(int var, bool subst, int sym_bytes);
 int long_blocks_per_sm();

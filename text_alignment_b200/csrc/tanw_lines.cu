@@ -1,6 +1,9 @@
 // tanw_lines.cu -- instantiations of the four-pairs-per-warp line kernel (align_lines_kernel).
 #include "tanw_launch.h"
 
+#include <algorithm>
+#include "tanw_lines16.cuh"
+
 namespace tanw {
 
 template <bool SUBST, int VAR>
@@ -24,6 +27,23 @@ cudaError_t launch_lines(const LineArgs &a, const KParams &kp, int var, bool sub
     case 1:  return go<false, 1>(a, kp, grid, stream);
     default: return go<false, 0>(a, kp, grid, stream);
     }
+}
+
+cudaError_t launch_lines16(const LineArgs &a, const KParams &kp, int var, int grid, cudaStream_t stream)
+{
+    if (var == 2) align_lines16_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, kp);
+    else          align_lines16_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, kp);
+    return cudaGetLastError();
+}
+
+int lines16_blocks_per_sm()
+{
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_lines16_kernel<1>, kWarpsPerBlock * 32, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return occ;
 }
 
 int lines_blocks_per_sm()

@@ -28,11 +28,12 @@ constexpr int kTile = 2048;                        // pairs per block of survey_
 constexpr int kTileThreads = 256;
 constexpr int kTilePer = kTile / kTileThreads;     // consecutive pairs per thread
 constexpr int kMaxChunks = 16;                     // a batch call is pipelined in up to this many chunks
-constexpr int kLineKeys = 4 * (kLineMaxN + 1);     // line sort keys: 4 strip-width classes x (n + 1)
-constexpr int kPageKeys = 65536;                   // page sort keys: n*m quantised to 16 bits
+constexpr int kLineNKeys = 1024;                   // line sort keys: heights beyond this share the last key
+constexpr int kLineKeys = 4 * kLineNKeys;          // ... x 4 strip-width classes
+constexpr int kPageKeys = 4096;                    // page sort keys: n*m quantised to 12 bits
 constexpr int kMaxLongList = 4096;                 // chained-stripe pairs listed for the host per batch
 
-enum Route : int { kRoutePage = 0, kRouteLine = 1, kRouteLong = 2 };
+enum Route : int { kRoutePage = 0, kRouteLine = 1, kRouteLong = 2, kRouteLine16 = 3 };
 
 // What the host learns about one chunk of the batch (pairs [first, first + count)).
 struct ChunkSurvey {
@@ -43,10 +44,13 @@ struct ChunkSurvey {
     long long max_slot;         // largest ptr_bytes() among its page pairs
     long long max_line_slot;    // largest line_ptr_bytes() among its line pairs
     long long max_page_cells;   // largest n*m among its page pairs
+    long long max_line16_slot;  // largest line_ptr_bytes() among its pairs of the 16-bit line kernel
     int max_n_page;             // tallest page pair (boundary array rows)
-    int n_page, n_line, n_long;
+    int n_page, n_line, n_long, n_line16;
     int line_class[4];          // line pairs per strip-width class (cell-less pairs count as class 0)
-    int pad;
+    int line16_class[4];        // the same for the pairs of the 16-bit line kernel
+    int max_nm_line16;          // longest possible op string (n + m) among them
+    int max_n_line16;           // tallest of them
 };
 
 struct Survey {
@@ -66,6 +70,7 @@ struct TableArgs {
     long long long_cells;       // n*m >= this: chained stripes
     long long slot_limit;       // a page pair whose pointer bytes * warps per block exceed this: chained stripes
     int use_lines, wide, tiny_batch, can_long;
+    int line16_max_n;           // line pairs up to this height run two per register (tanw_lines16.cuh); 0: none
     // outputs
     Survey *survey;
     long long *tile_sums;       // per tile: sum of n+m
@@ -73,11 +78,11 @@ struct TableArgs {
     unsigned char *route;
     int *order;                 // page pairs of chunk c at order[c * chunk_pairs ...], largest first
     int *line_sorted;           // line pairs of chunk c at line_sorted[c * chunk_pairs ...]
-    int *hist;                  // per chunk: kLineKeys line bins, then kPageKeys page bins
-    LineClasses *classes;       // per chunk
+    int *hist;                  // per chunk: kLineKeys bins of the 16-bit line kernel, kLineKeys line bins, kPageKeys page bins
+    LineClasses *classes;       // per chunk: [2c] 16-bit line kernel (octets), [2c + 1] line kernel (quads)
 };
 
-constexpr int kHistStride = kLineKeys + kPageKeys;
+constexpr int kHistStride = 2 * kLineKeys + kPageKeys;
 
 __device__ __forceinline__ int route_of(const TableArgs &a, long long np, long long mp)
 {
@@ -86,14 +91,14 @@ __device__ __forceinline__ int route_of(const TableArgs &a, long long np, long l
                           !(!a.wide && a.use_lines && mp <= kLineMaxM && np <= kLineMaxN);
     const bool tiny = a.tiny_batch && mp > kLineMaxM && np * mp >= (1ll << 16);
     if ((np * mp >= a.long_cells || tiny || oversize) && a.can_long) return kRouteLong;
-    if (!a.wide && a.use_lines && mp <= kLineMaxM && np <= kLineMaxN) return kRouteLine;
+    if (!a.wide && a.use_lines && mp <= kLineMaxM && np <= kLineMaxN) return (a.line16_max_n > 0 && np <= a.line16_max_n) ? kRouteLine16 : kRouteLine;
     return kRoutePage;
 }
 
 __device__ __forceinline__ int line_key(int np, int mp)
 {
     const bool act = np > 0 && mp > 0;
-    return kLineKeys - 1 - ((act ? line_c(mp) / 4 - 1 : 0) * (kLineMaxN + 1) + (act ? np : 0));
+    return kLineKeys - 1 - ((act ? line_c(mp) / 4 - 1 : 0) * kLineNKeys + (act ? min(np, kLineNKeys - 1) : 0));
 }
 
 __device__ __forceinline__ long long block_sum(long long v, long long *sh)
@@ -118,8 +123,8 @@ __global__ void __launch_bounds__(kTileThreads) survey_kernel(const TableArgs a)
     __shared__ long long sh[kTileThreads / 32];
     const long long base = (long long)blockIdx.x * kTile + (long long)threadIdx.x * kTilePer;
     const int chunk = (int)(((long long)blockIdx.x * kTile) / a.chunk_pairs);
-    long long cap = 0, cells = 0, page_cells = 0, sym_end = 0, max_slot = 0, max_line = 0, max_pc = 0, bad = -1;
-    int max_n = 0, max_nm = 0, n_page = 0, n_line = 0, n_long = 0, cls[4] = {0, 0, 0, 0};
+    long long cap = 0, cells = 0, page_cells = 0, sym_end = 0, max_slot = 0, max_line = 0, max_line16 = 0, max_pc = 0, bad = -1;
+    int max_n = 0, max_nm = 0, max_nm16 = 0, max_n16 = 0, n_page = 0, n_line = 0, n_long = 0, n_line16 = 0, cls[4] = {0, 0, 0, 0}, cls16[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < kTilePer; ++k) {
         const long long p = base + k;
@@ -142,6 +147,12 @@ __global__ void __launch_bounds__(kTileThreads) survey_kernel(const TableArgs a)
             ++n_line;
             max_line = max(max_line, line_ptr_bytes((int)np, (int)mp));
             ++cls[(np > 0 && mp > 0) ? line_c((int)mp) / 4 - 1 : 0];
+        } else if (r == kRouteLine16) {
+            ++n_line16;
+            max_nm16 = max(max_nm16, (int)(np + mp));
+            max_n16 = max(max_n16, (int)np);
+            max_line16 = max(max_line16, line_ptr_bytes((int)np, (int)mp));
+            ++cls16[(np > 0 && mp > 0) ? line_c((int)mp) / 4 - 1 : 0];
         } else {
             ++n_page;
             page_cells += np * mp;
@@ -160,14 +171,21 @@ __global__ void __launch_bounds__(kTileThreads) survey_kernel(const TableArgs a)
         sym_end = max(sym_end, __shfl_down_sync(kFull, sym_end, d));
         max_slot = max(max_slot, __shfl_down_sync(kFull, max_slot, d));
         max_line = max(max_line, __shfl_down_sync(kFull, max_line, d));
+        max_line16 = max(max_line16, __shfl_down_sync(kFull, max_line16, d));
         max_pc = max(max_pc, __shfl_down_sync(kFull, max_pc, d));
         max_n = max(max_n, __shfl_down_sync(kFull, max_n, d));
         max_nm = max(max_nm, __shfl_down_sync(kFull, max_nm, d));
+        max_nm16 = max(max_nm16, __shfl_down_sync(kFull, max_nm16, d));
+        max_n16 = max(max_n16, __shfl_down_sync(kFull, max_n16, d));
         n_page += __shfl_down_sync(kFull, n_page, d);
         n_line += __shfl_down_sync(kFull, n_line, d);
         n_long += __shfl_down_sync(kFull, n_long, d);
+        n_line16 += __shfl_down_sync(kFull, n_line16, d);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cls[c] += __shfl_down_sync(kFull, cls[c], d);
+        for (int c = 0; c < 4; ++c) {
+            cls[c] += __shfl_down_sync(kFull, cls[c], d);
+            cls16[c] += __shfl_down_sync(kFull, cls16[c], d);
+        }
     }
     if (bad >= 0) atomicMax(&a.survey->bad, 0xFFFFFFFFFFFFFFFFull - (unsigned long long)bad);
     if ((threadIdx.x & 31) == 0) {
@@ -177,15 +195,21 @@ __global__ void __launch_bounds__(kTileThreads) survey_kernel(const TableArgs a)
         atomic_max_ll(&cs->sym_end, sym_end);
         atomic_max_ll(&cs->max_slot, max_slot);
         atomic_max_ll(&cs->max_line_slot, max_line);
+        atomic_max_ll(&cs->max_line16_slot, max_line16);
         atomic_max_ll(&cs->max_page_cells, max_pc);
         atomicMax(&cs->max_n_page, max_n);
         atomicMax(&a.survey->max_nm, max_nm);
+        atomicMax(&cs->max_nm_line16, max_nm16);
+        atomicMax(&cs->max_n_line16, max_n16);
         if (n_page) atomicAdd(&cs->n_page, n_page);
         if (n_line) atomicAdd(&cs->n_line, n_line);
         if (n_long) atomicAdd(&cs->n_long, n_long);
+        if (n_line16) atomicAdd(&cs->n_line16, n_line16);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c) {
             if (cls[c]) atomicAdd(&cs->line_class[c], cls[c]);
+            if (cls16[c]) atomicAdd(&cs->line16_class[c], cls16[c]);
+        }
     }
     if (threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.survey->chunk[chunk].cap), (unsigned long long)tile_cap);
@@ -242,23 +266,25 @@ __global__ void __launch_bounds__(kTileThreads) build_kernel(const TableArgs a, 
         off += (long long)np[k] + mp[k];
         const int r = route_of(a, np[k], mp[k]);
         a.route[p] = (unsigned char)r;
-        if (r == kRouteLine) atomicAdd(hist + line_key(np[k], mp[k]), 1);
+        if (r == kRouteLine16) atomicAdd(hist + line_key(np[k], mp[k]), 1);
+        else if (r == kRouteLine) atomicAdd(hist + kLineKeys + line_key(np[k], mp[k]), 1);
         else if (r == kRoutePage)
-            atomicAdd(hist + kLineKeys + (kPageKeys - 1 - (int)(((long long)np[k] * mp[k]) >> shift)), 1);
+            atomicAdd(hist + 2 * kLineKeys + (kPageKeys - 1 - (int)(((long long)np[k] * mp[k]) >> shift)), 1);
     }
 }
 
-// Exclusive prefix sums over the line bins and over the page bins of a chunk (one block), and
-// the strip-width classes of its line pairs.  Afterwards hist[1 + key] is the first slot of
-// `key` among the line pairs, hist[kLineKeys + key] among the page pairs.
-__global__ void __launch_bounds__(1024) bins_kernel(const TableArgs a, int chunk, int4 line_class)
+// Exclusive prefix sums over the line bins (16-bit kernel first, then the int32 line kernel: one
+// sorted list) and over the page bins of a chunk (one block), and the strip-width classes of its
+// line pairs.  Afterwards hist[key] / hist[kLineKeys + key] is the first slot of `key` in the
+// sorted line list, hist[2 * kLineKeys + key] among the page pairs.
+__global__ void __launch_bounds__(1024) bins_kernel(const TableArgs a, int chunk, int4 line16_class, int4 line_class)
 {
     __shared__ int sh[32];
     __shared__ int carry;
     int *hist = a.hist + (size_t)chunk * kHistStride;
     for (int part = 0; part < 2; ++part) {
-        int *h = hist + (part == 0 ? 0 : kLineKeys);
-        const int nb = part == 0 ? kLineKeys : kPageKeys;
+        int *h = hist + (part == 0 ? 0 : 2 * kLineKeys);
+        const int nb = part == 0 ? 2 * kLineKeys : kPageKeys;
         if (threadIdx.x == 0) carry = 0;
         __syncthreads();
         for (int b0 = 0; b0 < nb; b0 += 1024 * 4) {
@@ -298,18 +324,23 @@ __global__ void __launch_bounds__(1024) bins_kernel(const TableArgs a, int chunk
     }
     if (threadIdx.x == 0) {
         // line pairs are sorted by descending (class, n): class 3 first
-        const int count[4] = { line_class.x, line_class.y, line_class.z, line_class.w };
-        LineClasses lc;
-        int at = 0, quads = 0;
-        for (int c = 3; c >= 0; --c) {
-            lc.start[c] = at;
-            lc.count[c] = count[c];
-            lc.quad0[c] = quads;
-            at += count[c];
-            quads += (count[c] + 3) / 4;
+        int at = 0;
+        for (int kind = 0; kind < 2; ++kind) {           // 0: octets of the 16-bit kernel, 1: quads
+            const int4 cl = kind == 0 ? line16_class : line_class;
+            const int count[4] = { cl.x, cl.y, cl.z, cl.w };
+            const int per = kind == 0 ? 8 : 4;
+            LineClasses lc;
+            int units = 0;
+            for (int c = 3; c >= 0; --c) {
+                lc.start[c] = at;
+                lc.count[c] = count[c];
+                lc.quad0[c] = units;
+                at += count[c];
+                units += (count[c] + per - 1) / per;
+            }
+            lc.n_quads = units;
+            a.classes[2 * chunk + kind] = lc;
         }
-        lc.n_quads = quads;
-        a.classes[chunk] = lc;
     }
 }
 
@@ -322,11 +353,11 @@ __global__ void __launch_bounds__(kTileThreads) scatter_kernel(const TableArgs a
     int *hist = a.hist + (size_t)chunk * kHistStride;
     const int r = a.route[p];
     const int np = a.n[p], mp = a.m[p];
-    if (r == kRouteLine) {
-        const int at = atomicAdd(hist + line_key(np, mp), 1);
+    if (r == kRouteLine || r == kRouteLine16) {
+        const int at = atomicAdd(hist + (r == kRouteLine ? kLineKeys : 0) + line_key(np, mp), 1);
         a.line_sorted[first + at] = (int)p;
     } else if (r == kRoutePage) {
-        const int at = atomicAdd(hist + kLineKeys + (kPageKeys - 1 - (int)(((long long)np * mp) >> shift)), 1);
+        const int at = atomicAdd(hist + 2 * kLineKeys + (kPageKeys - 1 - (int)(((long long)np * mp) >> shift)), 1);
         a.order[first + at] = (int)p;
     }
 }
