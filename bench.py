@@ -620,6 +620,64 @@ def sharded_legs(h, args, state, npairs):
     return res
 
 
+def shim_leg(h, pairs, npairs):
+    """The Python list <-> buffer shim, reported separately (it is not the path)."""
+    from text_alignment_b200 import textSeqCompare as tsc_mod
+    k = min(2000, npairs)
+    lists = [(list(t), list(o)) for t, o in pairs[:k]]
+    tsc_mod.perform_alignment_batch(lists[:8], devices=[h.local_rank])
+    s0 = time.perf_counter()
+    tsc_mod.perform_alignment_batch(lists, devices=[h.local_rank])
+    s1 = time.perf_counter()
+    one = lists[0]
+    tsc_mod.perform_alignment(one[0], one[1])
+    s2 = time.perf_counter()
+    for _ in range(5):
+        tsc_mod.perform_alignment(one[0], one[1])
+    s3 = time.perf_counter()
+    # what CPython itself needs to touch the same lists once: the floor of any list-in / list-out API
+    f0 = time.perf_counter()
+    for t, o in lists:
+        ''.join(t); ''.join(o); list(''.join(t)); list(''.join(o))
+    f1 = time.perf_counter()
+    return dict(pages=k, ms_per_page=(s1 - s0) * 1e3 / k, pages_per_s=k / (s1 - s0),
+                single_call_ms=(s3 - s2) * 1e3 / 5, join_and_list_floor_ms_per_page=(f1 - f0) * 1e3 / k,
+                what='perform_alignment_batch on Python lists: one interning of the whole batch (CPython helper), '
+                     'one launch, op strings back to two lists per page; single_call_ms = perform_alignment on one '
+                     'page; floor = two str.join + two list(str) per page in pure Python, for scale')
+
+
+def consumer_leg(h):
+    """The consumer either side of the path: object path vs array path."""
+    from text_alignment_b200 import alignToOCR as atocr, latinSyllabification as latsyl, synth
+    cpages, seed = [], 70000
+    while len(cpages) < 200:
+        t, boxes = synth.make_page(seed, 1200, 1500)
+        seed += 1
+        try:
+            latsyl.syllabify_text(t)                 # a truncated last word may have no syllable seed
+        except ValueError:
+            continue
+        cpages.append((t, boxes))
+    arrays = [(t, ''.join(c for c, _, _ in boxes),
+               np.array([[ul[0], ul[1], lr[0], lr[1]] for _, ul, lr in boxes], dtype=np.int32)) for t, boxes in cpages]
+    atocr.boxes_for_pages_arrays(arrays[:8], devices=[h.local_rank])
+    s0 = time.perf_counter()
+    got = atocr.boxes_for_pages_arrays(arrays, devices=[h.local_rank])
+    s1 = time.perf_counter()
+    objs = [(t, [atocr.CharBox(c, ul, lr) for c, ul, lr in boxes]) for t, boxes in cpages[:16]]
+    s2 = time.perf_counter()
+    ref = atocr.boxes_for_pages(objs, devices=[h.local_rank])
+    s3 = time.perf_counter()
+    same = all([b.char for b in r[0]] == g[0] and [[b.ulx, b.uly, b.lrx, b.lry] for b in r[0]] == g[1].tolist()
+               for r, g in zip(ref, got))
+    return dict(pages=len(arrays), array_path_ms_per_page=(s1 - s0) * 1e3 / len(arrays),
+                object_path_ms_per_page=(s3 - s2) * 1e3 / len(objs), identical=bool(same),
+                what='transcript + OCR character boxes -> syllable boxes (alignToOCR.py:247-324) for c2-sized '
+                     'pages, alignment on the device: boxes_for_pages_arrays (native, arrays) vs boxes_for_pages '
+                     '(CharBox objects + one regex per syllable, as the reference)')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -668,48 +726,18 @@ def main():
     # ---- the Python list <-> buffer shim, reported separately (it is not the path) ----
     shim = None
     if rank == 0 and args.workload in ('c2', 'c4', 'c1'):
-        from text_alignment_b200 import textSeqCompare as tsc_mod
-        k = min(2000, npairs)
-        lists = [(list(t), list(o)) for t, o in state['pairs'][:k]]
-        tsc_mod.perform_alignment_batch(lists[:8], devices=[h.local_rank])
-        s0 = time.perf_counter()
-        tsc_mod.perform_alignment_batch(lists, devices=[h.local_rank])
-        s1 = time.perf_counter()
-        one = lists[0]
-        tsc_mod.perform_alignment(one[0], one[1])
-        s2 = time.perf_counter()
-        for _ in range(5):
-            tsc_mod.perform_alignment(one[0], one[1])
-        s3 = time.perf_counter()
-        shim = dict(pages=k, ms_per_page=(s1 - s0) * 1e3 / k, pages_per_s=k / (s1 - s0),
-                    single_call_ms=(s3 - s2) * 1e3 / 5,
-                    what='perform_alignment_batch on Python lists: interning to uint8 codes, one launch, '
-                         'op strings back to two lists per page; single_call_ms = perform_alignment on one page')
+        try:
+            shim = shim_leg(h, state['pairs'], npairs)
+        except Exception as e:                       # noqa: BLE001
+            shim = dict(error=repr(e))
 
     # ---- the consumer either side of the path: object path vs array path ----------------
     consumer = None
     if rank == 0 and args.workload == 'c2' and not args.no_others:
-        from text_alignment_b200 import alignToOCR as atocr, synth
-        cpages = [synth.make_page(70000 + k, 1200, 1500) for k in range(200)]
-        arrays = []
-        for t, boxes in cpages:
-            arrays.append((t, ''.join(c for c, _, _ in boxes),
-                           np.array([[ul[0], ul[1], lr[0], lr[1]] for _, ul, lr in boxes], dtype=np.int32)))
-        atocr.boxes_for_pages_arrays(arrays[:8], devices=[h.local_rank])
-        s0 = time.perf_counter()
-        got = atocr.boxes_for_pages_arrays(arrays, devices=[h.local_rank])
-        s1 = time.perf_counter()
-        objs = [(t, [atocr.CharBox(c, ul, lr) for c, ul, lr in boxes]) for t, boxes in cpages[:16]]
-        s2 = time.perf_counter()
-        ref = atocr.boxes_for_pages(objs, devices=[h.local_rank])
-        s3 = time.perf_counter()
-        same = all([b.char for b in r[0]] == g[0] and [[b.ulx, b.uly, b.lrx, b.lry] for b in r[0]] == g[1].tolist()
-                   for r, g in zip(ref, got))
-        consumer = dict(pages=len(arrays), array_path_ms_per_page=(s1 - s0) * 1e3 / len(arrays),
-                        object_path_ms_per_page=(s3 - s2) * 1e3 / len(objs), identical=bool(same),
-                        what='transcript + OCR character boxes -> syllable boxes (alignToOCR.py:247-324) for c2-sized '
-                             'pages, alignment on the device: boxes_for_pages_arrays (native, arrays) vs boxes_for_pages '
-                             '(CharBox objects + one regex per syllable, as the reference)')
+        try:
+            consumer = consumer_leg(h)
+        except Exception as e:                       # noqa: BLE001  (a side leg must not cost the headline line)
+            consumer = dict(error=repr(e))
 
     # ---- the other BASELINE configs, short legs ------------------------------------------------------
     others = None
@@ -746,7 +774,11 @@ def main():
 
     sharded = None
     if world > 1 and not args.no_sharded:
-        sharded = sharded_legs(h, args, state, npairs)
+        try:
+            sharded = sharded_legs(h, args, state, npairs)
+        except Exception as e:                       # noqa: BLE001
+            sharded = dict(error=repr(e))
+            h.cpu_barrier()
 
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()

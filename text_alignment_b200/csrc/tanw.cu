@@ -492,7 +492,11 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ta.n_pairs = P;
     ta.symbols_len = in.symbols_len;
     // the survey reports on kMaxChunks slices of the batch; the host merges them into chunks
-    const int64_t slice_pairs = std::max<int64_t>(((P + kMaxChunks - 1) / kMaxChunks + kTile - 1) / kTile * kTile, kTile);
+    // a slice is at least what the 16-bit line kernel's resident warps align in one round (eight pairs
+    // per warp), so that the chunks of a batch of lines are whole rounds of the GPU
+    const int64_t round_pairs = (int64_t)ctx->sm_count * ctx->occ_line16 * kWarpsPerBlock * 8 / kTile * kTile;
+    const int64_t slice_pairs = std::max<int64_t>(std::max<int64_t>(((P + kMaxChunks - 1) / kMaxChunks + kTile - 1) / kTile * kTile,
+                                                                    round_pairs), kTile);
     ta.chunk_pairs = slice_pairs;
     ta.long_cells = ctx->long_cells;
     ta.slot_limit = limit;
@@ -773,6 +777,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     la.ops = a.ops;
     la.ops_len = a.ops_len;
     la.scores = a.scores;
+    la.check = a.check;
 
     ctx->n_pairs = P;
     ctx->ops_total = cap_total;

@@ -134,6 +134,13 @@ __device__ __forceinline__ int table_code(int v, const KParams &kp)
 //      first-index argmax (case analysis in DESIGN.md 4.1).  W and Q disappear: two maxes and
 //      one register per column less, D is one VIMNMX3.
 //   2  variant 1 with gap_extend_y == 0 (the reference's default_sys): no Y + ey add.
+//   3, 4  variants 1, 2 for the chained-stripe kernel, where a stripe is ONE warp bound by the
+//      latency of the dependent chain along a row, not by issue slots: X as in variant 1 (from D),
+//      but Y from Q = max(M, X) as the reference writes it (max(M+oy, X+oy, Y+ey), :75-80), so that
+//      the chain from a cell to its right neighbour is  Y -> max(Q+oy, Y+ey) -> clean  (two
+//      dependent instructions) instead of  Y -> D = max3(M, X, Y) -> max(D+oy, Y+ey) -> clean.
+//      Same instruction count (VIADDMNMX + VIMNMX for VIADD + VIMNMX3), one more of them on the
+//      alu pipe -- which is why the batched kernels, bound by that pipe, keep variants 1 / 2.
 template <int C>
 struct Strip {
     int W[C];         // general variant only: max(M|tagM, Y) of the row above
@@ -154,8 +161,9 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
                                           int &q_out, int &y_out, unsigned (&pw)[C / 4],
                                           int kfin, int (&cap)[3])
 {
-    constexpr bool FAST = (VAR >= 1);
-    constexpr bool EYZ = (VAR == 2);
+    constexpr bool FAST = (VAR >= 1);                 // X from D: no W
+    constexpr bool YQ = (VAR == 0 || VAR >= 3);       // Y from Q = max(M, X); the edge carries (Q, Y)
+    constexpr bool EYZ = (VAR == 2 || VAR == 4);
     const int *srow = SUBST ? kp.subst + tch * kp.subst_k : nullptr;
     int q = q_in;                             // general: Q of the cell to the left; FAST: its D
     int ypl = EYZ ? y_in : y_in + kp.ey;      // Y of the column to the left, + ey
@@ -186,13 +194,13 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
         const int yraw = __viaddmax_s32(q, kp.oy, ypl);
         const int yc = clean_tag(yraw);
         int dn, qn;
-        if (FAST) {
+        if (!YQ) {
             dn = __vimax3_s32(m2, xh + xe, yc);              // max(M, X, Y)
             qn = dn;
         } else {
             qn = __viaddmax_s32(xh, xe, m2);                 // max(M, X)
             dn = max(qn, yc);                                // max(M, X, Y)
-            s.W[k] = max(yc, m2);                            // max(M, Y)
+            if (!FAST) s.W[k] = max(yc, m2);                 // max(M, Y)
         }
         // pointer byte: scores are multiples of 64, so the low six bits of
         // dul + 4*xraw + 16*yraw are exactly tagM | tagX<<2 | tagY<<4 (two IMADs); bits 6-7 are
@@ -358,7 +366,7 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
             ps.bnext = __ldcg(ps.bp);             // same address in every lane
         }
     }
-    const int dul_in = (VAR >= 1) ? ps.q_prev : max(ps.q_prev, ps.y_prev);   // D of (i-1, left neighbour column)
+    const int dul_in = (VAR == 1 || VAR == 2) ? ps.q_prev : max(ps.q_prev, ps.y_prev);   // D of (i-1, left neighbour column)
     const int tch = ps.tnext;
     if (CHAINED) {
         // a stripe has its scheduler to itself: one step does not cover the load latency
@@ -897,6 +905,7 @@ struct LineArgs {
     uint8_t        *ops;
     int            *ops_len;
     int            *scores;
+    int            *check;       // TANW_CHECKED builds: first failed device assertion (0 = none)
 };
 
 struct LineState {
@@ -1022,6 +1031,7 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
     }
     const bool act = (n > 0 && m > 0);
     if (!act) { T = a.sym; O = a.sym; }
+    TANW_ASSERT(a.check, !act || (line_ptr_bytes(n, m) <= a.slot_bytes && m <= kLineG * C), 5);
     // tallest / shortest active pair of the quad (n is uniform inside a group)
     int nmax = act ? n : 0, nmin = act ? n : 0x7fffffff;
 #pragma unroll

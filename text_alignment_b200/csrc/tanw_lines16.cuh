@@ -348,6 +348,10 @@ __device__ __forceinline__ void line_octet(const LineArgs &a, const KParams &kp3
     const uint8_t *TA = a.sym + cur.dA.t_off, *OA = a.sym + cur.dA.o_off;
     const uint8_t *TB = a.sym + cur.dB.t_off, *OB = a.sym + cur.dB.o_off;
     const bool actA = nA > 0 && mA > 0, actB = nB > 0 && mB > 0;
+    TANW_ASSERT(a.check, (!actA || (line_ptr_bytes(nA, mA) <= a.slot_bytes && mA <= kLineG * C)) &&
+                (!actB || (line_ptr_bytes(nB, mB) <= a.slot_bytes && mB <= kLineG * C)), 6);
+    // every half stays inside [0, 65535]: (2n + m + 4) * max|param| <= kRange16 (the host's routing rule)
+    TANW_ASSERT(a.check, (2 * max(nA, nB) + kLineMaxM + 4) * max(max(abs(kp.ox), abs(kp.ex)), max(abs(kp.bg), (int)kp.dmul)) / 4 <= 2 * kRange16, 7);
     // tallest / shortest active pair of the octet
     int nmax = max(actA ? nA : 0, actB ? nB : 0), nmin = min(actA ? nA : 0x7fffffff, actB ? nB : 0x7fffffff);
     const bool all_act = __all_sync(kFull, actA && actB);

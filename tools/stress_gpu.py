@@ -1,9 +1,21 @@
-"""Randomised stress of every kernel family against the C oracle (seeded; prints a summary)."""
+"""Randomised stress of every kernel family against the C oracle (seeded; prints a summary).
+
+    python tools/stress_gpu.py [rounds] [seed] [--lib path/to/libtanw_checked.so]
+
+With --lib the run uses another build of the library -- the TANW_CHECKED build
+(`__graft_entry__.build_library(out, defines=['TANW_CHECKED'])`), whose device assertions (arena
+bounds of every pointer slot, op-string lengths, stamped hand-over records, bounded spins, the
+16-bit range rule) turn into an AssertionError here; compute-sanitizer is closed on this pool."""
 import os, sys, random, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from text_alignment_b200 import _native
 from oracle import nw_oracle
+if '--lib' in sys.argv:
+    at = sys.argv.index('--lib')
+    _native.load(sys.argv[at + 1])
+    del sys.argv[at:at + 2]
+    print('library:', _native._lib._name)
 
 def pack(pairs):
     buf = np.frombuffer(''.join(t + o for t, o in pairs).encode('latin-1'), dtype=np.uint8)
@@ -50,6 +62,7 @@ for rd in range(rounds):
     if len(pairs) <= 25 and shape != 'tall':
         band_ctx.set_long_band_rows(rng.choice([3, 17, 40, 64, 129, 300]))
         use.append(band_ctx)
+    ctx.set_line_kernel(rng.choice([1, 1, 2, 0]))
     for c in use:
         got = c.align_batch(*b, c.make_scoring(*params))
         assert np.array_equal(got[2], want[2]), (rd, shape, params)
@@ -58,4 +71,29 @@ for rd in range(rounds):
             assert np.array_equal(got[0][got[1][k]:got[1][k]+got[2][k]], want[0][want[1][k]:want[1][k]+want[2][k]]), (rd, shape, params, k, b[2][k], b[4][k])
     total += len(pairs) * len(use)
     print('round', rd, shape, len(pairs), 'pairs', params, 'ok', flush=True)
+# a big batch of lines: the chunked pipeline of tanw_align_batch, and per-pair scoring systems
+ctx.set_line_kernel(1)
+pairs = []
+for _ in range(60000):
+    n, m = rng.randint(1, 125), rng.randint(1, 130)
+    t = ''.join(rng.choice('abcdefghil ') for _ in range(n))
+    pairs.append((t, t[:m] + ''.join(rng.choice('abcdefghil ') for _ in range(max(0, m - n)))))
+b = pack(pairs)
+sc, _ = nw_oracle.make_scoring([8, -4, -7, -7, -3, 0], boundary_gap=-1)
+want = nw_oracle.align_batch_codes(*b, sc, threads=16)
+got = ctx.align_batch(*b, ctx.make_scoring(8, -4, -7, -7, -3, 0, -1))
+assert ctx.timing()['chunks'] > 1 and np.array_equal(got[2], want[2])
+for k in range(0, len(pairs), 7):
+    assert np.array_equal(got[0][got[1][k]:got[1][k]+got[2][k]], want[0][want[1][k]:want[1][k]+want[2][k]]), k
+total += len(pairs)
+systems = [(8, -4, -7, -7, -3, 0, -1), (5, -4, -2, -7, 0, -5, -1), (7, 2, 3, -4, -1, 1, -1)]
+sub = pack(pairs[:300])
+idx = np.array([rng.randrange(3) for _ in range(300)], dtype=np.int32)
+got = ctx.align_batch_multi(*sub, systems, idx)
+for s_i, prm in enumerate(systems):
+    sc, _ = nw_oracle.make_scoring(list(prm[:6]), boundary_gap=prm[6])
+    want = nw_oracle.align_batch_codes(*sub, sc, threads=16)
+    for k in np.nonzero(idx == s_i)[0]:
+        assert np.array_equal(got[0][got[1][k]:got[1][k]+got[2][k]], want[0][want[1][k]:want[1][k]+want[2][k]]), (s_i, k)
+total += 300
 print('stress ok: %d alignments, %.1f s' % (total, time.time() - t0))
