@@ -591,11 +591,14 @@ def sharded_legs(h, args, state, npairs):
                 weak=(big_p, toff, ns, ms, [g[3] for g in gathered]),
                 strong=(state['pinned'][0], t_off, n, m, [gathered[0][3]])).items():
             oo = to + nn
-            for _ in range(2):
-                r = tsc.align_packed(sy, to, nn, oo, mm, DEFAULT_PARAMS, devices=devices)
+            cap_all = int((nn.astype(np.int64) + mm).sum())
+            pout = (h.pinned_empty(max(cap_all, 1), np.uint8), h.pinned_empty(nn.size, np.int32),
+                    h.pinned_empty(nn.size * 3, np.int32, (nn.size, 3)))
+            for _ in range(3):
+                r = tsc.align_packed(sy, to, nn, oo, mm, DEFAULT_PARAMS, devices=devices, out=pout)
             t0 = time.perf_counter()
             for _ in range(steps):
-                r = tsc.align_packed(sy, to, nn, oo, mm, DEFAULT_PARAMS, devices=devices)
+                r = tsc.align_packed(sy, to, nn, oo, mm, DEFAULT_PARAMS, devices=devices, out=pout)
             ms_step = (time.perf_counter() - t0) * 1e3 / steps
             # bit-exact against what each rank got on its own device
             ok = True

@@ -213,6 +213,13 @@ int  tanw_measure_int32_peak(tanw_ctx *ctx, int which, double *lane_ops_per_s);
  * tanw_consumer_last_error() (thread-local). */
 const char *tanw_consumer_last_error(void);
 
+/* latinSyllabification.syllabify_text (latinSyllabification.py:22-109, :170-174) on bytes: the
+ * syllables of `text` (words = what split(' ') gives) as [first, one-past-last) character ranges,
+ * 2 ints per syllable.  ASCII letters, digits and spaces only: anything else returns TANW_E_STATE
+ * and the caller syllabifies in Python.  A word without a vowel -- on which the reference never
+ * terminates -- is TANW_E_INVALID.  *n_out = number of syllables (also when `capacity` was too small). */
+int  tanw_syllabify_text(const char *text, int64_t text_len, int32_t *bounds, int64_t capacity, int64_t *n_out);
+
 /* One text line of `ocropus-rpred --llocs` output (alignToOCR.py:153-182): UTF-8 records
  * "<character> TAB <x of its RIGHT edge inside the strip> NEWLINE".  A character's box runs from
  * the previous record's x to its own (np.round(x + x_min), half to even) over the strip's full

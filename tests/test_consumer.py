@@ -321,3 +321,34 @@ def test_array_consumer_on_gpu_llocs_to_json(golden):
         want = json.dumps({'median_line_spacing': 140.0,
                            'syl_boxes': [{'syl': s, 'ul': ul, 'lr': lr} for s, ul, lr in p['syl_boxes']]})
         assert atocr.to_JSON_bytes(syls, boxes, peaks) == want.encode()
+
+
+def test_native_syllabifier_equals_python(golden):
+    """csrc/tanw_consumer.cu restates latinSyllabification on bytes: same syllables on the golden
+    words (which come from the reference itself), on random letter salads, on whole texts; the same
+    refusal of a word without a vowel; non-ASCII text is left to the Python syllabifier."""
+    from text_alignment_b200 import _native
+    for word, want in golden['syllables']:
+        if not (word.isascii() and (word == '' or word.isalnum())):
+            continue
+        if want is None:
+            with pytest.raises(ValueError):
+                _native.syllable_bounds(word)
+        else:
+            assert [word[a:b] for a, b in _native.syllable_bounds(word).tolist()] == want, word
+    rng = random.Random(1)
+    for k in range(20000):
+        w = ''.join(rng.choice('aeiouyqchpflrstbxt' if k % 2 else 'abcdefghijklmnopqrstuvwxyz') for _ in range(rng.randint(1, 12)))
+        try:
+            want = latsyl.syllabify_word(w)
+        except ValueError:
+            want = None
+        if want is None:
+            with pytest.raises(ValueError):
+                _native.syllable_bounds(w)
+        else:
+            assert [w[a:b] for a, b in _native.syllable_bounds(w).tolist()] == want, w
+    text = 'quaecumque ejus  michi antiphonum assistens alleluya dixit extra exhibeamus euouae cuius eius '
+    assert [text[a:b] for a, b in _native.syllable_bounds(text).tolist()] == latsyl.syllabify_text(text)
+    assert _native.syllable_bounds(u'dūs') is None and _native.syllable_bounds('glo.ria') is None
+    assert _native.syllable_bounds('').shape == (0, 2)

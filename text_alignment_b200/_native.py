@@ -68,6 +68,7 @@ SIGNATURES = {
     'tanw_last_timing': (ctypes.c_int, [_VOIDP, ctypes.POINTER(Timing)]),
     'tanw_stream_handle': (ctypes.c_int, [_VOIDP, ctypes.POINTER(ctypes.c_uint64)]),
     'tanw_consumer_last_error': (ctypes.c_char_p, []),
+    'tanw_syllabify_text': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64, _i32p, ctypes.c_int64, _i64p]),
     'tanw_parse_llocs': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.POINTER(ctypes.c_uint32), _i32p, ctypes.c_int64, _i64p]),
     'tanw_syllable_boxes': (ctypes.c_int, [ctypes.c_int64, _u8p, _i64p, _i32p, _i32p, _i64p, _i32p, _i64p, _i32p, _u8p]),
@@ -158,6 +159,25 @@ def _consumer_check(rc):
         if 'all_chars not same length' in msg:
             raise AssertionError(msg)          # the reference's own assertion (alignToOCR.py:291)
         raise ValueError(msg)
+
+
+def syllable_bounds(text):
+    """Syllables of an ASCII transcript as int32[S, 2] character ranges, natively; None when the
+    text holds anything but ASCII letters, digits and spaces (the caller then uses the Python
+    syllabifier); ValueError for a word without a vowel, as the Python syllabifier."""
+    lib = load()
+    try:
+        raw = text.encode('ascii')
+    except UnicodeEncodeError:
+        return None
+    cap = len(raw) + 1
+    bounds = np.empty((cap, 2), dtype=np.int32)
+    k = ctypes.c_int64(0)
+    rc = lib.tanw_syllabify_text(raw, len(raw), _ptr(bounds, _i32p), cap, ctypes.byref(k))
+    if rc == 6:
+        return None
+    _consumer_check(rc)
+    return bounds[:k.value]
 
 
 def parse_llocs(text, x_min, y_min, y_max):
@@ -327,7 +347,7 @@ class Context(object):
         ops_off, total = layout if layout is not None else self.canonical_ops_layout(n, m)
         if out is not None:
             ops, ops_len, scores = out
-            if ops.size < total or ops_len.size < P or (want_scores and scores.size < 3 * P):
+            if (ops.size < total and total > 0) or ops_len.size < P or (want_scores and scores.size < 3 * P):
                 raise ValueError('preallocated output buffers are too small')
         else:
             ops = np.empty(max(total, 1), dtype=np.uint8)

@@ -215,6 +215,9 @@ def syllable_spans(transcript):
     Words are what ``split(' ')`` gives (latinSyllabification.py:171); a word's syllables are
     consecutive pieces of it (None is returned if that ever fails to hold, and the caller keeps
     the regular-expression path)."""
+    bounds = _native.syllable_bounds(transcript)
+    if bounds is not None:                                   # the native syllabifier (ASCII text)
+        return [transcript[a:b] for a, b in bounds.tolist()], bounds
     words = transcript.split(' ')
     per_word = [_word_syllables(w) for w in words]
     syls = [s for ws in per_word for s in ws]

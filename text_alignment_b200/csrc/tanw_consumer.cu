@@ -17,6 +17,7 @@
 // Plain C ABI like the rest of the library (include/tanw.h); no device work, no context.
 #include "tanw.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -108,9 +109,140 @@ bool json_string(Out &o, const unsigned char *s, const unsigned char *end)
 
 }  // namespace
 
+// ---- Latin syllabification (latinSyllabification.py:22-109, :170-174) on bytes ------------------------
+// The reference cuts a word into units -- consonant clusters, then diphthongs, each class in its
+// listed order and each occurrence taken left to right as str.split does; what is left falls apart
+// into single letters -- marks vowels and diphthongs as seeds, and then, until only seeds remain,
+// glues every non-seed unit directly before a seed onto it and after that every non-seed unit
+// directly after a seed.  Units are contiguous pieces of the word, so a unit is (start, length, flag).
+struct Unit { int start, len; bool done, seed; };   // done: taken out by a pattern (no further cuts)
+
+const char *const kClusters[] = { "qu", "ch", "ph", "fl", "fr", "st", "br", "cr", "cl", "pr", "tr", "ct", "th",
+                                  "ae", "au", "ei", "oe", "ui", "ya", "ex", "ix" };
+constexpr int kConsonantGroups = 13, kPatterns = 21;
+constexpr int kMaxWord = 512;
+
+bool is_vowel(char c) { return c == 'a' || c == 'e' || c == 'i' || c == 'o' || c == 'u' || c == 'y'; }
+
+// Syllables of word[0..len) as lengths; returns their number, -1 if the word has no seed (the
+// reference never terminates on such a word), -2 if it is too long for the fixed buffers.
+int syllabify_word_bytes(const char *w, int len, int *out_len)
+{
+    if (len == 0) return 0;
+    if (len > kMaxWord) return -2;
+    // latinSyllabification.py:30-35
+    if (len == 6 && memcmp(w, "euouae", 6) == 0) { out_len[0] = 1; out_len[1] = 1; out_len[2] = 1; out_len[3] = 1; out_len[4] = 2; return 5; }
+    if (len == 5 && memcmp(w, "cuius", 5) == 0) { out_len[0] = 2; out_len[1] = 3; return 2; }
+    if (len == 4 && memcmp(w, "eius", 4) == 0) { out_len[0] = 1; out_len[1] = 3; return 2; }
+    static thread_local Unit a[kMaxWord + 2], b[kMaxWord + 2];
+    Unit *cur = a, *nxt = b;
+    int n = 1;
+    cur[0] = { 0, len, false, false };
+    for (int p = 0; p < kPatterns; ++p) {
+        const char c0 = kClusters[p][0], c1 = kClusters[p][1];
+        int k = 0;
+        for (int u = 0; u < n; ++u) {
+            const Unit part = cur[u];
+            if (part.done) { nxt[k++] = part; continue; }
+            int pos = part.start;
+            const int end = part.start + part.len;
+            for (int q = pos; q + 1 < end;) {
+                if (w[q] == c0 && w[q + 1] == c1) {
+                    if (q > pos) nxt[k++] = { pos, q - pos, false, false };
+                    nxt[k++] = { q, 2, true, p >= kConsonantGroups };
+                    q += 2;
+                    pos = q;
+                } else {
+                    ++q;
+                }
+            }
+            if (end > pos) nxt[k++] = { pos, end - pos, false, false };
+        }
+        Unit *t = cur; cur = nxt; nxt = t;
+        n = k;
+    }
+    // single letters; vowels and diphthongs are seeds (:66-68)
+    int k = 0;
+    bool any_seed = false;
+    for (int u = 0; u < n; ++u) {
+        if (cur[u].done) {
+            nxt[k] = cur[u];
+            nxt[k].done = false;
+            any_seed = any_seed || nxt[k].seed;
+            ++k;
+        } else {
+            for (int q = 0; q < cur[u].len; ++q) {
+                const bool v = is_vowel(w[cur[u].start + q]);
+                nxt[k++] = { cur[u].start + q, 1, false, v };
+                any_seed = any_seed || v;
+            }
+        }
+    }
+    { Unit *t = cur; cur = nxt; nxt = t; }
+    n = k;
+    if (!any_seed) return -1;
+    // glue until every unit is a seed (:71-105)
+    for (;;) {
+        bool all = true;
+        for (int u = 0; u < n; ++u) all = all && cur[u].seed;
+        if (all) break;
+        for (int pass = 0; pass < 2; ++pass) {                  // consonant + seed, then seed + consonant
+            k = 0;
+            for (int i = 0; i < n;) {
+                if (i + 1 < n) {
+                    const bool as = cur[i].seed, bs = cur[i + 1].seed;
+                    if (pass == 0 ? (bs && !as) : (as && !bs)) {
+                        nxt[k++] = { cur[i].start, cur[i].len + cur[i + 1].len, false, true };
+                        i += 2;
+                        continue;
+                    }
+                }
+                nxt[k++] = cur[i++];
+            }
+            Unit *t = cur; cur = nxt; nxt = t;
+            n = k;
+        }
+    }
+    for (int u = 0; u < n; ++u) out_len[u] = cur[u].len;
+    return n;
+}
+
 extern "C" {
 
 const char *tanw_consumer_last_error(void) { return g_consumer_error.c_str(); }
+
+int tanw_syllabify_text(const char *text, int64_t text_len, int32_t *bounds, int64_t capacity, int64_t *n_out)
+{
+    if (!n_out || (text_len > 0 && !text) || text_len < 0 || capacity < 0 || (capacity > 0 && !bounds))
+        return cfail(TANW_E_INVALID, "tanw_syllabify_text: bad argument");
+    int64_t count = 0;
+    static thread_local int lens[kMaxWord + 2];
+    for (int64_t i = 0; i <= text_len;) {
+        int64_t j = i;
+        while (j < text_len && text[j] != ' ') {
+            const unsigned char c = (unsigned char)text[j];
+            const bool alnum = (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
+            if (!alnum) return cfail(TANW_E_STATE, "character 0x%02x at %lld: the byte path takes ASCII letters, digits and spaces", c, (long long)j);
+            ++j;
+        }
+        const int k = syllabify_word_bytes(text + i, (int)std::min<int64_t>(j - i, kMaxWord + 1), lens);
+        if (k == -1) {
+            std::string word(text + i, (size_t)(j - i));
+            return cfail(TANW_E_INVALID, "cannot syllabify '%s': no vowel (the reference loops forever here)", word.c_str());
+        }
+        if (k == -2) return cfail(TANW_E_STATE, "word of %lld characters at %lld", (long long)(j - i), (long long)i);
+        int64_t at = i;
+        for (int u = 0; u < k; ++u) {
+            if (count < capacity) { bounds[2 * count] = (int32_t)at; bounds[2 * count + 1] = (int32_t)(at + lens[u]); }
+            at += lens[u];
+            ++count;
+        }
+        i = j + 1;
+    }
+    *n_out = count;
+    if (count > capacity) return cfail(TANW_E_NOMEM, "%lld syllables, capacity %lld", (long long)count, (long long)capacity);
+    return TANW_OK;
+}
 
 int tanw_parse_llocs(const char *text, int64_t text_len, int32_t x_min, int32_t y_min, int32_t y_max,
                      uint32_t *chars, int32_t *boxes, int64_t capacity, int64_t *n_out)

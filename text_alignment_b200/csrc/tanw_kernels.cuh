@@ -577,72 +577,85 @@ constexpr int kTileRows = 64;                      // rows of a traceback tile (
 constexpr int kTileWords = 16;                     // 64 columns of a traceback tile
 constexpr int kTileStride = kTileWords + 1;        // words per tile row in shared memory (+ pad)
 
-// Traceback of one pair (textSeqCompare.py:96-164) by one warp.  The pointer chase is a chain
-// of dependent loads, so the warp first pulls the 64-row x 64-column tile of pointer bytes
-// whose bottom-right corner is the current cell into shared memory (lane r: rows x-r and
-// x-32-r, 32 independent word loads), then lane 0 walks inside the tile.  Ops are written back
-// to front at the END of the pair's op buffer (capacity n+m); returns the number of columns
-// (valid in every lane).
-// The tile loop: walks from local cell (x, y) in state st (-1: take mat_ptr first) until the top
-// row or the left column of this pointer block is reached; x, y, st, k are updated in every lane.
+// Traceback of one whole-manuscript pair (textSeqCompare.py:96-164) by one warp (trace_long_kernel).
+// Nothing else runs beside it, so both halves of a tile's cost are in the open:
+//   * the load of the 64-row x 64-column tile whose bottom-right corner is the current cell: lane l
+//     takes word column wq_hi - (l & 15) and rows x - 32*(l >> 4) - r, r = 0..31 -- one cursor seek
+//     per lane, then 32 independent loads whose addresses differ by a constant (round 1 walked a
+//     cursor along the row for every load: ~700 instructions per lane and tile, as long as the
+//     DRAM round trip itself);
+//   * the walk inside the tile.  A path is mostly runs: diagonal steps whose pointer says "from
+//     M" again, or a long OCR insertion whose pointer says "extend" again.  While the state does
+//     not change, the next cell is known, so lane l looks at the l-th cell ahead in the current
+//     direction, a ballot finds the first lane whose pointer leaves the state, and the whole run
+//     -- up to 32 steps -- is taken at once; its (identical) ops are written by the lanes in
+//     parallel.  Round 1 walked one cell per ~70 cycles of dependent instructions.
+// Measured and dropped (config 5, 19.9 ms with this form): asking the L2 for the rows above the tile
+// (prefetch.global.L2 of rows x-40 .. x-127, 32 word columns) while the tile's own loads are in
+// flight -- 21.4 ms: 2 800 scattered prefetches per tile cost more than the round trip they hide;
+// the same from a second warp through a shared-memory mailbox -- the spinning warp slows the
+// walker's own shared-memory loads.
+// Ops are written back to front at the END of the pair's op buffer (capacity n+m); x, y, st, k are
+// updated in every lane.  st = -1: take mat_ptr of the start cell first (:102).
 __device__ __forceinline__ void traceback_core(const uint8_t *ptr, int n, int m, int cfull,
                                                uint8_t *ops_end, unsigned *tile, int lane,
                                                int &x, int &y, int &st, int &k)
 {
     const PtrMap map(n, m, cfull);
+    const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
     while (x > 0 && y > 0) {
-        // ---- tile load: word columns wq_hi-15 .. wq_hi, rows x-lane and x-32-lane ----------
+        // ---- tile load: word columns wq_hi-15 .. wq_hi, rows x .. x-63 ---------------------------
         const int wq_hi = (y - 1) >> 2;
-        const int row0 = x - lane, row1 = x - 32 - lane;
-        unsigned w0[kTileWords], w1[kTileWords];
-        PtrCursor cur;
-        cur.seek(map, wq_hi);
+        const int q = 15 - (lane & 15);                      // this lane's word column of the tile
+        const int wq = wq_hi - (lane & 15);
+        const int row_hi = x - 32 * (lane >> 4);             // its first row (it goes up from there)
+        unsigned w[32];
+        if (wq >= 0) {
+            PtrCursor cur;
+            cur.seek(map, wq);
+            const uint8_t *base = ptr + cur.rowless;
+            const long long step = 32ll * cur.C;
 #pragma unroll
-        for (int q = kTileWords - 1; q >= 0; --q) {
-            const int wq = wq_hi - (kTileWords - 1 - q);
-            w0[q] = 0u; w1[q] = 0u;
-            if (wq >= 0) {
-                if (row0 >= 1) w0[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row0)));
-                if (row1 >= 1) w1[q] = __ldcg(reinterpret_cast<const unsigned *>(ptr + cur.at_row(row1)));
-                if (wq > 0) cur.left(map);
+            for (int r = 0; r < 32; ++r) {
+                w[r] = 0u;
+                if (row_hi - r >= 1) w[r] = __ldcg(reinterpret_cast<const unsigned *>(base + (long long)(row_hi - r) * step));
             }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) w[r] = 0u;
         }
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < kTileWords; ++q) {
-            tile[lane * kTileStride + q] = w0[q];
-            tile[(lane + 32) * kTileStride + q] = w1[q];
-        }
+        for (int r = 0; r < 32; ++r) tile[(32 * (lane >> 4) + r) * kTileStride + q] = w[r];
         __syncwarp();
-        // ---- walk inside the tile ---------------------------------------------------------
-        // state 0: diagonal, next = mat_ptr; 1: x-gap, next = x_mat_ptr; 2: y-gap, next =
-        // y_mat_ptr (:115-145).  One lane, a chain of dependent shared-memory loads: the loop
-        // keeps only  load -> shift -> mask -> subtract  on that chain (byte-addressed tile,
-        // running offset, exit counters that do not depend on the loaded byte).
-        if (lane == 0) {
-            const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
-            const int col_lo = (wq_hi - (kTileWords - 1)) * 4;      // 0-based column of tile byte 0
-            int off = (y - 1) - col_lo;                             // row 0 of the tile, 60..63
-            if (st < 0) st = 2 - (int)(tb[off] & 3u);                                 // :102
-            const int xr0 = min(x, kTileRows), yr0 = min(y, off + 1);
-            int xr = xr0, yr = yr0;                                 // row / column moves left here
-            while (xr > 0 && yr > 0) {
-                const unsigned b = tb[off];
-                const int dx = (st != 2), dy = (st != 1);
-                ++k;
-                *(ops_end - k) = (uint8_t)st;
-                off += dx * (kTileStride * 4) - dy;
-                xr -= dx;
-                yr -= dy;
-                st = 2 - (int)((b >> (2 * st)) & 3u);
-            }
-            x -= xr0 - xr;
-            y -= yr0 - yr;
+        // ---- walk inside the tile, a run per iteration -----------------------------------------------
+        // tile row R = matrix row x - R; tile byte column c = matrix column (col_lo + c + 1)
+        const int col_lo = (wq_hi - (kTileWords - 1)) * 4;          // 0-based matrix column of tile byte 0
+        const int rows_avail = min(x, kTileRows);
+        const int c_min = max(0, -col_lo);                          // tile column of matrix column 1
+        int R = 0, c = (y - 1) - col_lo;
+        if (st < 0) st = 2 - (int)(tb[c] & 3u);                                           // :102
+        for (;;) {
+            const int dx = (st != 2), dy = (st != 1);
+            const int Rl = R + lane * dx, cl = c - lane * dy;
+            const bool valid = Rl < rows_avail && cl >= c_min;
+            int nxt = -1;
+            if (valid) nxt = 2 - (int)((tb[Rl * (kTileStride * 4) + cl] >> (2 * st)) & 3u);
+            const unsigned same = __ballot_sync(kFull, valid && nxt == st);
+            const unsigned val = __ballot_sync(kFull, valid);
+            const int run = (same == kFull) ? 32 : __ffs(~same) - 1; // leading lanes that stay in the state
+            const bool turns = run < 32 && ((val >> run) & 1u);      // the run ends on a cell that changes the state
+            const int steps = turns ? run + 1 : run;
+            if (steps == 0) break;                                   // the next cell is outside the tile
+            if (lane < steps) *(ops_end - (k + 1 + lane)) = (uint8_t)st;                  // :115-145
+            k += steps;
+            R += steps * dx;
+            c -= steps * dy;
+            if (turns) st = __shfl_sync(kFull, nxt, run);
+            if (R >= rows_avail || c < c_min) break;
         }
-        x = __shfl_sync(kFull, x, 0);
-        y = __shfl_sync(kFull, y, 0);
-        st = __shfl_sync(kFull, st, 0);
-        k = __shfl_sync(kFull, k, 0);
+        x -= R;
+        y = col_lo + c + 1;
     }
 }
 

@@ -475,12 +475,15 @@ def split_by_cells(n, m, parts):
     return np.maximum.accumulate(np.clip(bounds, 0, P))
 
 
-def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, want_scores=True):
+def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, want_scores=True, out=None):
     """Packed-buffer entry: uint8 (or uint16) codes + offsets in, op strings out (include/tanw.h layout).
 
     params = (match, mismatch, gap_open_x, gap_open_y, gap_extend_x, gap_extend_y, boundary_gap).
     devices: list of CUDA device indices; the batch is cut into contiguous, cell-balanced
-    shards, one host thread + context + stream per device, results gathered by pair index."""
+    shards, one host thread + context + stream per device.  Shards are contiguous ranges of pairs,
+    so every device writes its results straight into its slice of the batch's output arrays: the
+    "host-side gather" of SURVEY.md 8(e) is the layout itself, no copy.
+    out = (ops, ops_len, scores) preallocated (e.g. page-locked) arrays for the whole batch."""
     if devices is None:
         devices = [0]
     devices = list(devices)
@@ -493,18 +496,33 @@ def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, 
     if len(devices) == 1 or n.size < 2:
         ctx = get_context(devices[0])
         return ctx.align_batch(symbols, t_off, n, o_off, m, ctx.make_scoring(*params, subst=subst),
-                               want_scores=want_scores)
+                               want_scores=want_scores, out=out)
+    P = int(n.size)
     bounds = split_by_cells(n, m, len(devices))
-    outs = [None] * len(devices)
+    ops_off, total = _native.Context.canonical_ops_layout(n, m)
+    if out is not None:
+        ops, ops_len, scores = out
+        if ops.size < total or ops_len.size < P or (want_scores and scores.size < 3 * P):
+            raise ValueError('preallocated output buffers are too small')
+    else:
+        ops = np.empty(max(total, 1), dtype=np.uint8)
+        ops_len = np.zeros(max(P, 1), dtype=np.int32)
+        scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
     errs = [None] * len(devices)
 
     def work(d):
         lo, hi = int(bounds[d]), int(bounds[d + 1])
+        if hi <= lo:
+            return
         try:
             ctx = get_context(devices[d], replica=devices[:d].count(devices[d]))
             sub_sym, sub_t, sub_o = _rebase(symbols, t_off[lo:hi], n[lo:hi], o_off[lo:hi], m[lo:hi])
-            outs[d] = ctx.align_batch(sub_sym, sub_t, n[lo:hi], sub_o, m[lo:hi],
-                                      ctx.make_scoring(*params, subst=subst), want_scores=want_scores)
+            base = int(ops_off[lo])
+            end = int(ops_off[hi]) if hi < P else total
+            shard_out = (ops[base:max(end, base + 1)], ops_len[lo:hi],
+                         scores.reshape(-1, 3)[lo:hi] if want_scores else None)
+            ctx.align_batch(sub_sym, sub_t, n[lo:hi], sub_o, m[lo:hi], ctx.make_scoring(*params, subst=subst),
+                            want_scores=want_scores, out=shard_out, layout=(ops_off[lo:hi] - base, end - base))
         except BaseException as e:       # re-raised on the caller's thread
             errs[d] = e
     threads = [threading.Thread(target=work, args=(d,)) for d in range(len(devices))]
@@ -515,7 +533,7 @@ def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, 
     for e in errs:
         if e is not None:
             raise e
-    return gather_shards(outs, n, m, want_scores, bounds)
+    return ops, ops_off, ops_len[:P], (scores.reshape(-1, 3)[:P] if want_scores else None)
 
 
 def _rebase(symbols, t_off, n, o_off, m):
