@@ -48,9 +48,7 @@ struct K16 {
     unsigned oy_simd;    // simd form of 4 * (gap_open_y + gap_extend_y)
     unsigned ey_add;     // packed for 32-bit adds: 4 * gap_extend_y
     int ox, ex, bg;      // 4 * (gap_open_x + gap_extend_x), 4 * gap_extend_x, 4 * boundary gap
-    unsigned tagx, zero; // kTagX16 and 0 in registers the compiler cannot see through: LOP3 takes one
-                         // immediate only, and a literal 0 as third operand of VIADDMNMX.S16x2 cost a PRMT
-                         // per cell (seen in the SASS of the first version)
+    unsigned tagx;       // kTagX16 in a register the compiler cannot see through: LOP3 takes one immediate only
 };
 
 __host__ __device__ inline unsigned pk_add(int c) { return (unsigned)c * 0x10001u; }          // (c << 16) + c
@@ -60,7 +58,6 @@ __device__ __forceinline__ K16 make_k16(const KParams &kp)
 {
     K16 k;
     asm volatile("mov.b32 %0, 0x00010001;" : "=r"(k.tagx));
-    asm volatile("mov.b32 %0, 0;" : "=r"(k.zero));
     const int match = kp.maT >> kShift, mismatch = kp.miT >> kShift;       // the tag bits fall off
     k.mi_add = pk_add(4 * mismatch + kTagM);
     k.dmul = (unsigned)(4 * (match - mismatch));
@@ -103,7 +100,7 @@ __device__ __forceinline__ void strip_row16(Strip16<C> &s, const K16 &kp, unsign
         // score: 1 per half where the symbols are equal (~(o ^ t) = -1 - (o ^ t) as a signed half)   (:31-32)
         unsigned e;
         asm("lop3.b32 %0, %1, %2, 0, 0xC3;" : "=r"(e) : "r"(s.oc[k]), "r"(tch2));                     // ~(a ^ b)
-        const unsigned eq = __viaddmax_s16x2(e, 0x00020002u, kp.zero);
+        const unsigned eq = __viaddmax_s16x2_relu(e, 0x00020002u, e);      // max(e + 2, e, 0): no zero operand to materialise
         // M[i][j] = max(M,X,Y)[i-1][j-1] + score, tagged M                                          (:70-72)
         const unsigned dc = dul & kClean16;
         const unsigned m2 = eq * kp.dmul + (dc + kp.mi_add);

@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Summarise an Nsight Compute report into a small text file for profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_align_pairs.txt [cells]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r2_align_pairs.txt [cells] [workload pairs]
+
+With `workload pairs` (e.g. `c2 10000`) the DRAM bytes of the first profiled launch are also
+recorded in profiles/traffic.json together with a digest of the kernel sources, which is where
+bench.py takes `roofline.traffic` from (and marks it stale once the kernels change).
 
 Keeps the metrics the roofline discussion in DESIGN.md refers to, the stall breakdown and the
 executed-instruction mix per opcode (from the source page; needs -lineinfo / --import-source)."""
@@ -71,6 +75,28 @@ def main():
                 lines.append('    %8s  %s' % (r[ix[col]], r[ix['Source']].strip()[:90]))
     open(dst, 'w').write('\n'.join(lines) + '\n')
     print('wrote', dst)
+    if len(sys.argv) > 5:
+        import json
+        import os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        import bench
+        first = rows[2]
+        scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+        total = 0.0
+        for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(name)
+            total += float(first[i].replace(',', '')) * scale.get(units[i], 1.0)
+        path = os.path.join(root, 'profiles', 'traffic.json')
+        try:
+            tab = json.load(open(path))
+        except (OSError, ValueError):
+            tab = {}
+        tab[sys.argv[4]] = dict(pairs=int(sys.argv[5]), dram_bytes_per_launch=total,
+                                kernel=first[hdr.index('Kernel Name')], digest=bench.source_digest(),
+                                source=os.path.relpath(dst, root))
+        json.dump(tab, open(path, 'w'), indent=1, sort_keys=True)
+        print('updated', path)
 
 
 if __name__ == '__main__':
