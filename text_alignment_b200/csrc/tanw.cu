@@ -12,7 +12,9 @@
 //   s_k2   the page kernel of a chunk, beside the chunk's line kernels on s_k (disjoint parts of the
 //          pointer arena): a batch of lines always has a few pairs that are pages, and their kernel
 //          -- one warp per pair, ~50 us however few they are -- fills the tail of the line kernel
-//          instead of following it;
+//          instead of following it.  A batch of pages is cut in two chunks whose kernels alternate
+//          between s_k2 and s_k3 (two pointer arenas): the second kernel's blocks move in as the
+//          first one's retire, while the first chunk's results travel and the second's inputs arrive;
 //   s_out  device -> host copies of a chunk's op strings / lengths / scores while the next
 //          chunk is being aligned.
 // tanw_align_batch cuts a batch whose copies matter (10^5 short line pairs: 40 MB of copies for
@@ -105,7 +107,7 @@ struct LongPair {
 struct tanw_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_k3 = nullptr, s_out = nullptr;
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr,
                 ev_d2h0 = nullptr, ev_d2h1 = nullptr, ev_tab = nullptr, ev_survey = nullptr, ev_idle = nullptr;
     cudaEvent_t ev_piece[kPieces] = {}, ev_chunk[kMaxChunks] = {}, ev_fork[kMaxChunks] = {}, ev_pages[kMaxChunks] = {};
@@ -124,6 +126,8 @@ struct tanw_ctx {
     KParams *h_kparams = nullptr;         // pinned: per-pair scoring systems of a multi batch
     size_t h_kparams_cap = 0;
     int line_mode = 1;                    // 0: no line kernels, 1: both, 2: the int32 line kernel only
+    bool alternate = false;               // page kernels of successive chunks on s_k2 / s_k3, arenas of their own
+    int64_t page_slots = 0;               // warp slots of one page arena
     int line16_max_n = 0;                 // tallest pair of the prepared batch on the 16-bit line kernel (0: none)
     int long_capacity = 0;                // resident warps for a cooperative launch
     int long_epoch = 0;                   // stamps the chain records of a launch
@@ -491,12 +495,8 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ta.m = (const int *)ctx->d_m.p;
     ta.n_pairs = P;
     ta.symbols_len = in.symbols_len;
-    // the survey reports on kMaxChunks slices of the batch; the host merges them into chunks
-    // a slice is at least what the 16-bit line kernel's resident warps align in one round (eight pairs
-    // per warp), so that the chunks of a batch of lines are whole rounds of the GPU
-    const int64_t round_pairs = (int64_t)ctx->sm_count * ctx->occ_line16 * kWarpsPerBlock * 8 / kTile * kTile;
-    const int64_t slice_pairs = std::max<int64_t>(std::max<int64_t>(((P + kMaxChunks - 1) / kMaxChunks + kTile - 1) / kTile * kTile,
-                                                                    round_pairs), kTile);
+    // the survey reports on up to kMaxSlices slices of the batch; the host merges them into chunks
+    const int64_t slice_pairs = std::max<int64_t>(((P + kMaxSlices - 1) / kMaxSlices + kTile - 1) / kTile * kTile, kTile);
     ta.chunk_pairs = slice_pairs;
     ta.long_cells = ctx->long_cells;
     ta.slot_limit = limit;
@@ -595,17 +595,33 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         n_page_total += cs.n_page; n_line_total += cs.n_line;
     }
     int S = 1;
+    int per = n_slices;                                  // slices per chunk
+    bool alternate = false;                              // page kernels of successive chunks on two streams
     if (in.pipelined && n_slices > 1 && ctx->longs.empty() && !sc->subst) {
-        // Chunks pay when the copies are long next to what a chunk boundary costs: a few small
-        // launches for a chunk of lines, and the idle tail of a page launch (about one page's
-        // alignment) for a chunk of pages.
         const double copy_ms = (double)(sym_bytes_total + cap_total) / 45e6;
-        double edge_ms = 0.03;
-        if (n_page_total > 0) edge_ms += (double)page_cells / n_page_total / 0.7e6 * 0.5;   // a warp aligns ~0.7e6 cells per ms
-        const double want = std::sqrt(copy_ms / edge_ms);
-        while (S * 2 <= n_slices && S * 2 <= want) S *= 2;
+        const int64_t page_warps = (int64_t)ctx->sm_count * ctx->occ_plain * kWarpsPerBlock;
+        if (n_page_total == 0 || page_cells * 20 < cells) {
+            // Lines (with the odd page among them): chunks pay when the copies are long next to what
+            // a chunk boundary costs (a few small launches), and a chunk should be whole rounds of
+            // the line kernel's resident warps (eight pairs each).
+            const double want = std::sqrt(copy_ms / 0.03);
+            while (S * 2 <= std::min<int>(n_slices, kMaxChunks) && S * 2 <= want) S *= 2;
+            if (S > 1) {
+                const double per_round = (double)ctx->sm_count * ctx->occ_line16 * kWarpsPerBlock * 8 / (double)slice_pairs;
+                const double rounds = std::max(1.0, std::floor((double)n_slices / S / per_round + 0.5));
+                per = (int)std::max(1.0, std::floor(rounds * per_round));
+                if ((n_slices + per - 1) / per > kMaxChunks) per = (n_slices + kMaxChunks - 1) / kMaxChunks;
+            }
+        } else if (n_line_total == 0 && n_page_total >= 3 * page_warps && copy_ms > 0.02 * (double)cells / 1.6e9) {
+            // Pages: two chunks whose kernels run on two streams with pointer arenas of their own,
+            // so that the second kernel's blocks move in as the first one's retire (no idle tail
+            // between them) while the first chunk's results travel and the second's inputs arrive.
+            S = 2;
+            per = (n_slices + 1) / 2;
+            alternate = true;
+        }
+        if (S == 1) per = n_slices;
     }
-    const int per = (n_slices + S - 1) / S;              // slices per chunk
     S = (n_slices + per - 1) / per;
     ctx->n_chunks = S;
     int64_t ops_base = 0;
@@ -645,7 +661,16 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->batch_sym_bytes = sb;
 
     // ---- launch geometry and scratch ----------------------------------------------------------
-    const int occ = ctx->use_subst ? ctx->occ_subst : ctx->occ_plain;
+    int occ = ctx->use_subst ? ctx->occ_subst : ctx->occ_plain;
+#ifdef TANW_TUNING
+    if (const char *e = getenv("TANW_PAGE_BLOCKS")) occ = std::max(1, std::min(occ, atoi(e)));   // tuning builds only
+#endif
+    // Few pairs per resident warp: the makespan is the largest pair on one warp, and a warp that
+    // shares its scheduler with three others runs at a quarter of the scheduler's rate.  Fewer CTAs
+    // per SM make every warp faster while the batch still fills them (config 4, 4 096 pairs:
+    // 4 / 3 / 2 CTAs per SM -> 6.03 / 5.82 / 5.73 ms; config 2, 10 000 pairs: 12.89 / 13.06 ms).
+    const double pages_in_flight = alternate ? (double)n_page_total : (double)max_page;      // alternating chunks share the GPU
+    while (occ > 2 && pages_in_flight / ((double)ctx->sm_count * occ * kWarpsPerBlock) < 2.5) --occ;
     int grid = ctx->sm_count * occ;
     const int64_t need_blocks = ((int64_t)max_page + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (need_blocks < grid) grid = (int)std::max<int64_t>(need_blocks, 1);
@@ -661,6 +686,9 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->grid = grid;
     ctx->slot_bytes = slot_bytes;
     const int64_t slots = (int64_t)grid * kWarpsPerBlock;
+    if (alternate && 2 * slots * slot_bytes > limit) alternate = false;       // one arena: the chunks' page kernels share a stream
+    ctx->alternate = alternate;
+    const int arenas = alternate ? 2 : 1;
     int line_grid = ctx->sm_count * ctx->occ_line;
     if (((int64_t)max_quads + kWarpsPerBlock - 1) / kWarpsPerBlock < line_grid)
         line_grid = (int)std::max<int64_t>(((int64_t)max_quads + kWarpsPerBlock - 1) / kWarpsPerBlock, 1);
@@ -685,8 +713,8 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         ctx->d_hist.reserve(sizeof(int) * (size_t)kHistStride * (size_t)S) != cudaSuccess ||
         ctx->d_classes.reserve(sizeof(LineClasses) * 2 * kMaxChunks) != cudaSuccess ||
         ctx->d_counter.reserve(sizeof(unsigned) * 4 * kMaxChunks) != cudaSuccess ||
-        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(slots * slot_bytes + line_arena, max_long), 256)) != cudaSuccess ||
-        ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(slots * bnd_rows, 1)) != cudaSuccess ||
+        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(arenas * slots * slot_bytes + line_arena, max_long), 256)) != cudaSuccess ||
+        ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(arenas * slots * bnd_rows, 1)) != cudaSuccess ||
         reserve_zeroed(ctx, ctx->d_chain, sizeof(int4) * (size_t)max_long_bnd) != cudaSuccess ||
         ctx->d_ck.reserve(sizeof(int) * (size_t)(4 + max_ck)) != cudaSuccess ||
         ctx->d_ops.reserve((size_t)cap_total + 64) != cudaSuccess ||
@@ -772,7 +800,8 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     memset(&la, 0, sizeof la);
     la.sym = a.sym;
     la.pairs = a.pairs;
-    la.ptr_arena = a.ptr_arena + (size_t)(slots * slot_bytes);        // behind the page kernel's slots
+    la.ptr_arena = a.ptr_arena + (size_t)(arenas * slots * slot_bytes);        // behind the page kernel's slots
+    ctx->page_slots = slots;
     la.slot_bytes = line_slot;
     la.ops = a.ops;
     la.ops_len = a.ops_len;
@@ -807,7 +836,7 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
         if (int rc = build_chunk_tables(ctx, c)) return rc;
         const ChunkPlan &cp = ctx->chunk[c];
         if (pipelined) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_piece[cp.piece], 0));
-        const bool forked = cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0);
+        const bool forked = cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0 || ctx->alternate);
         if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_fork[c], ctx->s_k));
         if (cp.n_octets > 0) {
             LineArgs la = ctx->largs;
@@ -836,11 +865,14 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             a.counter = (unsigned *)ctx->d_counter.p + 4 * c;
             a.n_pairs = cp.n_page;
             const int grid = (int)std::min<int64_t>(ctx->grid, ((int64_t)cp.n_page + kWarpsPerBlock - 1) / kWarpsPerBlock);
-            cudaStream_t st = forked ? ctx->s_k2 : ctx->s_k;
-            if (forked) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k2, ctx->ev_fork[c], 0));
+            const int parity = ctx->alternate ? (c & 1) : 0;
+            cudaStream_t st = forked ? (parity ? ctx->s_k3 : ctx->s_k2) : ctx->s_k;
+            a.ptr_arena += (size_t)parity * (size_t)(ctx->page_slots * ctx->slot_bytes);
+            a.bnd_arena += (size_t)parity * (size_t)(ctx->page_slots * a.bnd_rows);
+            if (forked) TANW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork[c], 0));
             TANW_CUDA(ctx, launch_pairs(a, ctx->kp, ctx->var, ctx->use_subst, ctx->batch_sym_bytes, ctx->multi,
                                         std::max(grid, 1), st));
-            if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_pages[c], ctx->s_k2));
+            if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_pages[c], st));
             ++launches;
         }
         cp_forked[c] = forked;
@@ -896,7 +928,7 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
     for (int c = 0; c < ctx->n_chunks; ++c) {
         const ChunkPlan &cp = ctx->chunk[c];
         TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_chunk[c], 0));
-        if (cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0))
+        if (cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0 || ctx->alternate))
             TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_pages[c], 0));
         if (c == 0) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h0, ctx->s_out));
         if (cp.cap > 0) {
@@ -1019,7 +1051,7 @@ int tanw_create(int device, tanw_ctx **out)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     DeviceGuard guard(device);
     cudaError_t e = guard.err;
-    cudaStream_t *streams[] = { &ctx->s_in, &ctx->s_k, &ctx->s_k2, &ctx->s_out };
+    cudaStream_t *streams[] = { &ctx->s_in, &ctx->s_k, &ctx->s_k2, &ctx->s_k3, &ctx->s_out };
     for (auto s : streams)
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = { &ctx->ev_h2d0, &ctx->ev_h2d1, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_d2h0, &ctx->ev_d2h1 };
@@ -1063,7 +1095,7 @@ int tanw_destroy(tanw_ctx *ctx)
 {
     if (!ctx) return TANW_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t streams[] = { ctx->s_in, ctx->s_k, ctx->s_k2, ctx->s_out };
+    cudaStream_t streams[] = { ctx->s_in, ctx->s_k, ctx->s_k2, ctx->s_k3, ctx->s_out };
     for (auto s : streams)
         if (s) cudaStreamSynchronize(s);
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_n, &ctx->d_m, &ctx->d_toff, &ctx->d_ooff, &ctx->d_pairs, &ctx->d_route,
@@ -1153,6 +1185,7 @@ int tanw_sync(tanw_ctx *ctx)
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k2));
+    TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k3));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return TANW_OK;
 }

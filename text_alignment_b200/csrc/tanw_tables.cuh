@@ -7,7 +7,7 @@
 // one host core: 1.6 ms per 125 000 line pairs, more than their 0.95 ms of alignment):
 //
 //   survey_kernel   per-pair validation and routing (line / page / chained-stripe kernel), sizes
-//                   of the scratch the batch needs, per-tile sums of n+m, for sixteen slices of the
+//                   of the scratch the batch needs, per-tile sums of n+m, for up to 64 slices of the
 //                   batch (the host merges slices into the chunks it pipelines); its 1 KB result
 //                   is the only thing the host waits for before it launches;
 //   build_kernel    exclusive prefix sums of n+m (the canonical op-buffer layout), the pair
@@ -27,7 +27,8 @@ namespace tanw {
 constexpr int kTile = 2048;                        // pairs per block of survey_kernel / build_kernel
 constexpr int kTileThreads = 256;
 constexpr int kTilePer = kTile / kTileThreads;     // consecutive pairs per thread
-constexpr int kMaxChunks = 16;                     // a batch call is pipelined in up to this many chunks
+constexpr int kMaxChunks = 16;                     // a batch call is pipelined in up to this many chunks ...
+constexpr int kMaxSlices = 64;                     // ... each made of slices the survey reports on
 constexpr int kLineNKeys = 1024;                   // line sort keys: heights beyond this share the last key
 constexpr int kLineKeys = 4 * kLineNKeys;          // ... x 4 strip-width classes
 constexpr int kPageKeys = 4096;                    // page sort keys: n*m quantised to 12 bits
@@ -57,7 +58,7 @@ struct Survey {
     unsigned long long bad;     // 0: every pair is valid; else ULLONG_MAX - (smallest invalid pair index)
     int max_nm;                 // largest n+m (range check of the fixed-point scores)
     int n_long;                 // entries in long_list (may exceed kMaxLongList: then the batch is refused)
-    ChunkSurvey chunk[kMaxChunks];
+    ChunkSurvey chunk[kMaxSlices];
     int long_list[kMaxLongList];
 };
 
