@@ -534,9 +534,37 @@ def measure(h, which, npairs, steps, warmup, parity_pairs, full):
         same = bool(np.array_equal(out[0][:ops_cap], out2[0][:ops_cap]))
         ctx_b.close()
 
-    vals = [dev_ms, e2e_ms, (w1 - w0) * 1e3] + ([pipe_ms] if full else [])
+    # ---- leg 4: end to end with packed op strings (four ops per byte on the way back) --------------
+    outp = out_buffers()
+    ctx.set_packed_ops(True)
+    try:
+        for _ in range(3):
+            ctx.align_batch(p_buf, p_toff, p_n, p_ooff, p_m, scoring, out=outp, layout=layout)
+        h.barrier()
+        z0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.align_batch(p_buf, p_toff, p_n, p_ooff, p_m, scoring, out=outp, layout=layout)
+        h.barrier()
+        packed_ms = (time.perf_counter() - z0) * 1e3
+        tmp = ctx.timing()
+    finally:
+        ctx.set_packed_ops(False)
+    if which != 'c5':
+        k = min(npairs, 2000)                    # unpack a sample on the host and compare with leg 2's bytes
+        got_ops, _ = ctx.unpack_ops(outp[0], n[:k], m[:k], outp[1][:k])
+        cap_k = int((n[:k].astype(np.int64) + m[:k]).sum())
+        ref_ops = np.zeros(max(cap_k, 1), dtype=np.uint8)
+        lens_k = out[1][:k].astype(np.int64)
+        off_k = layout[0][:k]
+        idx = np.repeat(off_k, lens_k) + (np.arange(int(lens_k.sum())) - np.repeat(np.cumsum(lens_k) - lens_k, lens_k))
+        ref_ops[idx] = out[0][idx]
+        packed_same = bool(np.array_equal(got_ops[:cap_k], ref_ops[:cap_k]) and np.array_equal(outp[1][:k], out[1][:k]))
+    else:
+        packed_same = bool(np.array_equal(outp[1][:npairs], out[1][:npairs]))
+
+    vals = [dev_ms, e2e_ms, (w1 - w0) * 1e3, packed_ms] + ([pipe_ms] if full else [])
     vals = h.max_over_ranks(vals)
-    dev_ms, e2e_ms, wall_ms = vals[:3]
+    dev_ms, e2e_ms, wall_ms, packed_ms = vals[:4]
     tot_cells, tot_pairs = h.sum_over_ranks([cells, npairs])
     gcups = tot_cells * steps / (dev_ms * 1e-3) / 1e9
     launch_s = dev_ms * 1e-3 / steps
@@ -552,9 +580,13 @@ def measure(h, which, npairs, steps, warmup, parity_pairs, full):
                                    host_prepare=tm['host_prepare_ms'], host_run=tm['host_run_ms'],
                                    host_fetch=tm['host_fetch_ms'])),
         achieved_ops=cells * OPS_PER_CELL / launch_s, achieved_gbs=cells * PTR_BYTES_PER_CELL / launch_s / 1e9)
+    frag['e2e']['packed_ops'] = dict(
+        value=tot_cells * steps / (packed_ms * 1e-3) / 1e9, unit='GCUPS', ms_per_step=packed_ms / steps,
+        d2h_bytes_per_step=int(tmp['d2h_bytes']), results_identical=packed_same,
+        how='the same call after tanw_set_packed_ops(1): op strings come back four to a byte')
     if full:
         frag['e2e']['double_buffered'] = dict(
-            value=tot_cells * steps / (vals[3] * 1e-3) / 1e9, unit='GCUPS', ms_per_step=vals[3] / steps,
+            value=tot_cells * steps / (vals[4] * 1e-3) / 1e9, unit='GCUPS', ms_per_step=vals[4] / steps,
             results_identical=same, how='two contexts alternate; each step = prepare (H2D) + run + fetch (D2H)')
     state = dict(packed=packed, pairs=pairs, out=out, pinned=(p_buf, p_toff, p_n, p_ooff, p_m), cells=cells)
     return frag, state
@@ -768,7 +800,10 @@ def main():
                 workload=WORKLOADS[which]['name'], n_gpus=1 if solo else world, value=f['value'], unit='GCUPS',
                 ms_per_step=f['ms_per_step'], pages_per_s=f['pages_per_s'], pairs_per_gpu=f['pairs_per_gpu'],
                 cells_per_gpu=f['cells_per_gpu'], steps=3, warmup=3, gpu_launches=f['gpu_launches'],
-                e2e=dict(value=f['e2e']['value'], ms_per_step=f['e2e']['ms_per_step'],
+                e2e=dict(value=f['e2e']['value'], ms_per_step=f['e2e']['ms_per_step'], chunks=f['e2e']['chunks'],
+                         packed_ops=dict(value=f['e2e']['packed_ops']['value'], ms_per_step=f['e2e']['packed_ops']['ms_per_step'],
+                                         d2h_bytes_per_step=f['e2e']['packed_ops']['d2h_bytes_per_step'],
+                                         results_identical=f['e2e']['packed_ops']['results_identical']),
                          h2d_bytes_per_step=f['e2e']['h2d_bytes_per_step'],
                          d2h_bytes_per_step=f['e2e']['d2h_bytes_per_step'], breakdown_ms=f['e2e']['breakdown_ms']),
                 roofline=dict(frac=f['achieved_ops'] / int32_peak, frac_of_alu_pipe=f['achieved_ops'] / alu_pipe_peak,

@@ -143,6 +143,14 @@ int  tanw_set_symbol_bytes(tanw_ctx *ctx, int bytes);
  * kernel only (same results on every route; used by the tests to compare them).  Default: 1. */
 int  tanw_set_line_kernel(tanw_ctx *ctx, int mode);
 
+/* Packed op strings: an op is 0, 1 or 2, so with enabled != 0 the batch calls deliver FOUR OPS PER
+ * BYTE -- op q of pair p in bits 2*(q & 3) of byte (ops_off_canonical[p] >> 2) + p + (q >> 2) of
+ * `ops`, where ops_off_canonical is the prefix sum of n+m (every pair starts on a fresh byte; no
+ * other layout is offered, `ops_off` is ignored) and `ops_capacity` must be at least
+ * sum(n+m)/4 + n_pairs + 1.  A quarter of the bytes cross PCIe on the way back, which is what
+ * bounds short-line batches on a box with eight GPUs.  Same alignments, another wire format. */
+int  tanw_set_packed_ops(tanw_ctx *ctx, int enabled);
+
 /* ---- one-call batch alignment: the entry the reference's call site maps to ------------------
  * Replaces N calls of textSeqCompare.perform_alignment (textSeqCompare.py:13) -- copies the
  * inputs to the device, runs fill + traceback, copies ops / lengths / scores back.

@@ -792,3 +792,37 @@ def test_line16_rescore_needs_an_eligible_system():
         _same_results(a, ctx.fetch(), len(pairs))
     finally:
         ctx.close()
+
+
+def test_packed_ops_are_the_same_alignments(oracle):
+    """tanw_set_packed_ops: four ops per byte on the way back (a quarter of the PCIe traffic);
+    unpacked, they are the bytes the default mode returns -- for lines (both line kernels), pages,
+    a chained-stripe pair, cell-less pairs, through the chunked pipeline and the three-phase form."""
+    from text_alignment_b200 import _native
+    pairs = [synth.c3_pair(k) for k in range(45000)] + [synth.c2_pair(k) for k in range(6)] + \
+            [('', 'abc'), ('abc', ''), ('', ''), synth.make_pair(3, 400, 90, 2, 6)]
+    buf, t_off, n, o_off, m = _pack(pairs)
+    ctx = _native.Context(0)
+    try:
+        ctx.set_long_threshold(2500000)                  # the largest page takes the chained-stripe path
+        sc = ctx.make_scoring(*DEFAULT)
+        plain = ctx.align_batch(buf, t_off, n, o_off, m, sc)
+        ctx.set_packed_ops(True)
+        packed = ctx.align_batch(buf, t_off, n, o_off, m, sc)             # one chunk: a chained-stripe pair is in it
+        assert packed[0].size == int((n.astype(np.int64) + m).sum()) // 4 + len(pairs) + 1
+        ctx.prepare(buf, t_off, n, o_off, m, sc)
+        ctx.run()
+        three = ctx.fetch()
+        ctx.set_long_threshold(1 << 26)
+        piped = ctx.align_batch(buf, t_off, n, o_off, m, sc)              # without it: the chunked pipeline
+        assert ctx.timing()['chunks'] > 1
+        ctx.set_packed_ops(False)
+        for got in (packed, three, piped):
+            assert np.array_equal(got[2], plain[2]) and np.array_equal(got[3], plain[3])
+            ops, off = ctx.unpack_ops(got[0], n, m, got[2])
+            assert np.array_equal(off, plain[1])
+            for k in list(range(0, len(pairs), 211)) + list(range(len(pairs) - 10, len(pairs))):
+                assert np.array_equal(ops[off[k]:off[k] + got[2][k]], plain[0][plain[1][k]:plain[1][k] + plain[2][k]]), k
+    finally:
+        ctx.close()
+    _ = oracle

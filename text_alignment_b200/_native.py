@@ -52,6 +52,7 @@ SIGNATURES = {
     'tanw_set_long_band_rows': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_set_symbol_bytes': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_set_line_kernel': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
+    'tanw_set_packed_ops': (ctypes.c_int, [_VOIDP, ctypes.c_int]),
     'tanw_align_batch': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                         ctypes.POINTER(Scoring), _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
     'tanw_align_batch_multi': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
@@ -248,6 +249,7 @@ class Context(object):
         self.device = int(device)
         self._keep = None
         self._sym_bytes = 1
+        self._packed = False
 
     def close(self):
         if getattr(self, '_h', None):
@@ -298,6 +300,38 @@ class Context(object):
         kernel only, 0 / False = the page kernel."""
         self._check(self._lib.tanw_set_line_kernel(self._h, int(mode)))
 
+    def set_packed_ops(self, enabled):
+        """Deliver op strings four to a byte (include/tanw.h, tanw_set_packed_ops); ``align_batch``
+        then returns the packed buffer, ``packed_layout`` / ``unpack_ops`` give the byte view back."""
+        with self.lock:
+            self._check(self._lib.tanw_set_packed_ops(self._h, 1 if enabled else 0))
+            self._packed = bool(enabled)
+
+    @staticmethod
+    def packed_layout(n, m):
+        """(packed offsets, packed total bytes) of a batch: (ops_off >> 2) + p, sum(n+m)/4 + P + 1."""
+        off, total = Context.canonical_ops_layout(n, m)
+        return (off >> 2) + np.arange(n.size, dtype=np.int64), total // 4 + int(n.size) + 1
+
+    @staticmethod
+    def unpack_ops(packed, n, m, ops_len):
+        """Packed op strings -> (ops, ops_off) in the canonical one-byte-per-op layout."""
+        off, total = Context.canonical_ops_layout(n, m)
+        poff, _ = Context.packed_layout(n, m)
+        ops = np.zeros(max(total, 1), dtype=np.uint8)
+        P = int(n.size)
+        if P == 0:
+            return ops, off
+        lens = ops_len[:P].astype(np.int64)
+        tot = int(lens.sum())
+        start = np.cumsum(lens) - lens
+        pair = np.repeat(np.arange(P), lens)
+        q = np.arange(tot, dtype=np.int64) - np.repeat(start, lens)
+        src = packed[np.repeat(poff, lens) + (q >> 2)]
+        ops[np.repeat(off, lens) + q] = (src >> ((q & 3) * 2).astype(np.uint8)) & 3
+        del pair
+        return ops, off
+
     @staticmethod
     def _canon(symbols, t_off, n, o_off, m):
         # uint16 codes stay 16 bits wide (pairs with more than 256 distinct elements); anything else is bytes
@@ -345,6 +379,8 @@ class Context(object):
         sc, keep = scoring
         P = int(n.size)
         ops_off, total = layout if layout is not None else self.canonical_ops_layout(n, m)
+        if self._packed:
+            total = total // 4 + P + 1           # the packed buffer (ops_off stays the canonical byte layout)
         if out is not None:
             ops, ops_len, scores = out
             if (ops.size < total and total > 0) or ops_len.size < P or (want_scores and scores.size < 3 * P):

@@ -118,7 +118,7 @@ struct tanw_ctx {
 
     DevBuf d_sym, d_n, d_m, d_toff, d_ooff, d_pairs, d_route, d_order, d_lsorted, d_hist, d_classes, d_tilesums,
            d_survey, d_counter, d_arena, d_bnd, d_ops, d_len, d_scores, d_subst, d_chain, d_ck, d_kparams, d_sidx,
-           d_misc;
+           d_misc, d_pack;
     Survey *h_survey = nullptr;           // pinned: the device's report on the batch
     int *h_misc = nullptr;                // pinned: [0] device assertion word, [1] largest symbol code
     int *h_subst = nullptr;               // pinned copy of the substitution table in kernel encoding
@@ -126,6 +126,8 @@ struct tanw_ctx {
     KParams *h_kparams = nullptr;         // pinned: per-pair scoring systems of a multi batch
     size_t h_kparams_cap = 0;
     int line_mode = 1;                    // 0: no line kernels, 1: both, 2: the int32 line kernel only
+    bool packed_ops = false;              // fetch delivers 2-bit packed op strings (tanw_set_packed_ops)
+    bool batch_packed = false;            // ... as the prepared batch was laid out
     bool alternate = false;               // page kernels of successive chunks on s_k2 / s_k3, arenas of their own
     int64_t page_slots = 0;               // warp slots of one page arena
     int line16_max_n = 0;                 // tallest pair of the prepared batch on the 16-bit line kernel (0: none)
@@ -398,6 +400,18 @@ int build_chunk_tables(tanw_ctx *ctx, int c)
     return TANW_OK;
 }
 
+// 2-bit packing of the op strings of a chunk's pairs with the given routes (tanw_tables.cuh).
+int pack_chunk(tanw_ctx *ctx, const ChunkPlan &cp, unsigned routes, cudaStream_t stream)
+{
+    if (cp.count <= 0) return TANW_OK;
+    const int blocks = (int)std::min<int64_t>((cp.count + 7) / 8, (int64_t)ctx->sm_count * 8);
+    pack_ops_kernel<<<blocks, 256, 0, stream>>>((const PairDesc *)ctx->d_pairs.p, (const unsigned char *)ctx->d_route.p,
+                                                (const int *)ctx->d_len.p, (const uint8_t *)ctx->d_ops.p,
+                                                (uint8_t *)ctx->d_pack.p, cp.first, cp.count, routes);
+    TANW_CUDA(ctx, cudaGetLastError());
+    return TANW_OK;
+}
+
 // ops_off is canonical when pair p's bytes start where pair p-1's capacity (n+m) ends.
 bool layout_is_canonical(const int64_t *ops_off, const int32_t *n, const int32_t *m, int64_t P)
 {
@@ -659,6 +673,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->var = var;
     ctx->max_nm = sv.max_nm;
     ctx->batch_sym_bytes = sb;
+    ctx->batch_packed = ctx->packed_ops;
 
     // ---- launch geometry and scratch ----------------------------------------------------------
     int occ = ctx->use_subst ? ctx->occ_subst : ctx->occ_plain;
@@ -696,7 +711,11 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->line_grid = line_grid;
     ctx->line_slot = line_slot;
     int64_t line_arena = max_quads ? (int64_t)line_grid * kWarpsPerBlock * 4 * line_slot : 0;
-    int line16_grid = ctx->sm_count * ctx->occ_line16;
+    int occ16 = ctx->occ_line16;
+#ifdef TANW_TUNING
+    if (const char *e = getenv("TANW_LINE16_BLOCKS")) occ16 = std::max(1, std::min(occ16, atoi(e)));   // tuning builds only
+#endif
+    int line16_grid = ctx->sm_count * occ16;
     if (((int64_t)max_octets + kWarpsPerBlock - 1) / kWarpsPerBlock < line16_grid)
         line16_grid = (int)std::max<int64_t>(((int64_t)max_octets + kWarpsPerBlock - 1) / kWarpsPerBlock, 1);
     const int64_t line16_slot = (max_line16_slot + 255) / 256 * 256;
@@ -718,6 +737,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         reserve_zeroed(ctx, ctx->d_chain, sizeof(int4) * (size_t)max_long_bnd) != cudaSuccess ||
         ctx->d_ck.reserve(sizeof(int) * (size_t)(4 + max_ck)) != cudaSuccess ||
         ctx->d_ops.reserve((size_t)cap_total + 64) != cudaSuccess ||
+        (ctx->packed_ops && ctx->d_pack.reserve((size_t)(cap_total / 4 + P + 64)) != cudaSuccess) ||
         ctx->d_len.reserve(sizeof(int) * Pz) != cudaSuccess ||
         ctx->d_scores.reserve(sizeof(int) * 3 * Pz) != cudaSuccess) {
         cudaGetLastError();
@@ -859,6 +879,10 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             TANW_CUDA(ctx, launch_lines(la, ctx->kp, ctx->var, ctx->use_subst, std::max(grid, 1), ctx->s_k));
             ++launches;
         }
+        if (ctx->batch_packed && (cp.n_octets > 0 || cp.n_quads > 0)) {
+            if (int rc = pack_chunk(ctx, cp, (1u << kRouteLine) | (1u << kRouteLine16), ctx->s_k)) return rc;
+            ++launches;
+        }
         if (cp.n_page > 0) {
             BatchArgs a = ctx->args;
             a.order = (const int *)ctx->d_order.p + cp.first;
@@ -872,8 +896,12 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             if (forked) TANW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork[c], 0));
             TANW_CUDA(ctx, launch_pairs(a, ctx->kp, ctx->var, ctx->use_subst, ctx->batch_sym_bytes, ctx->multi,
                                         std::max(grid, 1), st));
-            if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_pages[c], st));
             ++launches;
+            if (ctx->batch_packed) {
+                if (int rc = pack_chunk(ctx, cp, 1u << kRoutePage, st)) return rc;
+                ++launches;
+            }
+            if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_pages[c], st));
         }
         cp_forked[c] = forked;
         if (c + 1 == ctx->n_chunks) {
@@ -885,6 +913,10 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
                 const KParams kp = ctx->multi ? ctx->h_kparams[lp.sidx] : ctx->kp;
                 int rc = run_long_pair(ctx, lp, kp, ctx->var, &launches);
                 if (rc) return rc;
+            }
+            if (ctx->batch_packed && !ctx->longs.empty()) {
+                if (int rc = pack_chunk(ctx, cp, 1u << kRouteLong, ctx->s_k)) return rc;
+                ++launches;
             }
         }
         TANW_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[c], ctx->s_k));
@@ -904,8 +936,12 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
     const int64_t P = ctx->n_pairs;
     if (P > 0 && (!ops_off || !ops_len)) return fail(ctx, TANW_E_INVALID, "NULL output table");
     if (ctx->ops_total > 0 && !ops) return fail(ctx, TANW_E_INVALID, "ops is NULL");
+    const bool packed = ctx->batch_packed;
+    if (packed && ops_capacity < ctx->ops_total / 4 + P + 1)
+        return fail(ctx, TANW_E_INVALID, "packed op buffer too small: needs sum(n+m)/4 + pairs + 1 = %lld bytes",
+                    (long long)(ctx->ops_total / 4 + P + 1));
     // the common case first: the caller uses the canonical layout (prefix sums of n+m)
-    const bool canonical = layout_is_canonical(ops_off, n, m, P) && ctx->ops_total <= ops_capacity;
+    const bool canonical = packed || (layout_is_canonical(ops_off, n, m, P) && ctx->ops_total <= ops_capacity);
     if (!canonical) {
         for (int64_t p = 0; p < P; ++p) {
             const int64_t cap = (int64_t)n[p] + m[p];
@@ -931,7 +967,12 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
         if (cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0 || ctx->alternate))
             TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_pages[c], 0));
         if (c == 0) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h0, ctx->s_out));
-        if (cp.cap > 0) {
+        if (packed && cp.count > 0) {
+            const int64_t lo = (cp.ops_base >> 2) + cp.first, hi = ((cp.ops_base + cp.cap) >> 2) + cp.first + cp.count;
+            TANW_CUDA(ctx, cudaMemcpyAsync(dst + lo, (const uint8_t *)ctx->d_pack.p + lo, (size_t)(hi - lo),
+                                           cudaMemcpyDeviceToHost, ctx->s_out));
+            d2h += hi - lo;
+        } else if (cp.cap > 0) {
             TANW_CUDA(ctx, cudaMemcpyAsync(dst + cp.ops_base, (const uint8_t *)ctx->d_ops.p + cp.ops_base, (size_t)cp.cap,
                                            cudaMemcpyDeviceToHost, ctx->s_out));
             d2h += cp.cap;
@@ -1101,7 +1142,7 @@ int tanw_destroy(tanw_ctx *ctx)
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_n, &ctx->d_m, &ctx->d_toff, &ctx->d_ooff, &ctx->d_pairs, &ctx->d_route,
                        &ctx->d_order, &ctx->d_lsorted, &ctx->d_hist, &ctx->d_classes, &ctx->d_tilesums, &ctx->d_survey,
                        &ctx->d_counter, &ctx->d_arena, &ctx->d_bnd, &ctx->d_ops, &ctx->d_len, &ctx->d_scores,
-                       &ctx->d_subst, &ctx->d_chain, &ctx->d_ck, &ctx->d_kparams, &ctx->d_sidx, &ctx->d_misc };
+                       &ctx->d_subst, &ctx->d_chain, &ctx->d_ck, &ctx->d_kparams, &ctx->d_sidx, &ctx->d_misc, &ctx->d_pack };
     for (auto b : bufs) b->release();
     cudaEvent_t evs[] = { ctx->ev_h2d0, ctx->ev_h2d1, ctx->ev_k0, ctx->ev_k1, ctx->ev_d2h0, ctx->ev_d2h1,
                           ctx->ev_tab, ctx->ev_survey, ctx->ev_idle };
@@ -1158,6 +1199,14 @@ int tanw_set_long_band_rows(tanw_ctx *ctx, int rows)
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
     if (rows < 0) return fail(ctx, TANW_E_INVALID, "band height must be >= 0 rows");
     ctx->long_band_rows = rows;
+    ctx->prepared = false;
+    return TANW_OK;
+}
+
+int tanw_set_packed_ops(tanw_ctx *ctx, int enabled)
+{
+    if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
+    ctx->packed_ops = enabled != 0;
     ctx->prepared = false;
     return TANW_OK;
 }

@@ -363,6 +363,36 @@ __global__ void __launch_bounds__(kTileThreads) scatter_kernel(const TableArgs a
     }
 }
 
+// Packed op strings (tanw_set_packed_ops): an op is 0, 1 or 2, so four of them fit a byte.  Pair p's
+// packed string starts at byte (ops_off[p] >> 2) + p of the packed buffer -- a fresh byte for every
+// pair, no prefix sum needed (ceil((n+m)/4) <= (ops_off[p+1] >> 2) + 1 - (ops_off[p] >> 2)) -- op q in
+// bits 2*(q & 3) of byte q >> 2.  One warp per pair of the chunk whose route is in `routes` (bit r set
+// = route r), right after the kernels that aligned them, on their stream: a quarter of the bytes go
+// over PCIe (config 3 on 8 GPUs is bound by exactly that traffic).
+__global__ void __launch_bounds__(256) pack_ops_kernel(const PairDesc *pairs, const unsigned char *route, const int *ops_len,
+                                                       const uint8_t *ops, uint8_t *packed, long long first, long long count,
+                                                       unsigned routes)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long k = warp; k < count; k += warps) {
+        const long long p = first + k;
+        if (!((routes >> route[p]) & 1u)) continue;
+        const long long off = pairs[p].ops_off;
+        const int L = ops_len[p];
+        const uint8_t *src = ops + off;
+        uint8_t *dst = packed + (off >> 2) + p;
+        for (int j = lane; 4 * j < L; j += 32) {
+            unsigned b = src[4 * j];
+            if (4 * j + 1 < L) b |= (unsigned)src[4 * j + 1] << 2;
+            if (4 * j + 2 < L) b |= (unsigned)src[4 * j + 2] << 4;
+            if (4 * j + 3 < L) b |= (unsigned)src[4 * j + 3] << 6;
+            dst[j] = (uint8_t)b;
+        }
+    }
+}
+
 // The largest symbol code of the batch (tabulated scorers index a K x K table with them).
 template <typename SYM>
 __global__ void max_symbol_kernel(const SYM *sym, long long count, int *out)
