@@ -682,6 +682,65 @@ def shim_leg(h, pairs, npairs):
                      'page; floor = two str.join + two list(str) per page in pure Python, for scale')
 
 
+def extras_leg(h, state):
+    """Two paths the reference has and the headline does not exercise: its parameter sweep
+    (evaluate_text_alignment.py:134-194: 729 scoring vectors x 3 pages) as ONE launch with a scoring
+    system per pair, and a callable scorer (textSeqCompare.py:27-29) over a page batch, one launch with
+    the K x K table in shared memory, next to the equality scorer on the same pages."""
+    from itertools import product
+    from text_alignment_b200 import synth
+    ctx = h.ctx
+    out = {}
+    # -- the sweep: 3 c1-sized pages x 729 systems = 2187 pairs, one launch
+    grid = [(a, b, c, d, e, f, -1) for a, b, c, d, e, f in product([5, 8, 11], [-4, -7, -10], [-2, -5, -7], [-2, -5, -7],
+                                                                     [0, -3, -5], [0, -3, -5])]
+    pages = [synth.make_pair(1001 + k, 1200, 1500, 5, 40) for k in range(3)]
+    buf, t_off, n, o_off, m = pack_pairs(pages)
+    S, P = len(grid), len(pages)
+    args = (buf, np.tile(t_off, S), np.tile(n, S), np.tile(o_off, S), np.tile(m, S), grid, np.repeat(np.arange(S, dtype=np.int32), P))
+    for _ in range(2):
+        ctx.align_batch_multi(*args)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.align_batch_multi(*args)
+    wall = (time.perf_counter() - t0) / 3
+    tm = ctx.timing()
+    cells = int(S * (n.astype(np.int64) * m).sum())
+    out['sweep'] = dict(systems=S, pages=P, pairs=S * P, kernel_launches=int(tm['kernel_launches']),
+                        kernel_ms=tm['kernel_ms'], value=cells / (tm['kernel_ms'] * 1e-3) / 1e9, unit='GCUPS',
+                        e2e_ms=wall * 1e3, e2e_value=cells / wall / 1e9,
+                        what='evaluate_text_alignment.py:134-194 as one batch: per-pair scoring systems, pages uploaded once')
+    # -- a callable scorer: the table of f over the batch's alphabet, against the equality scorer
+    k = min(2000, len(state['pairs']))
+    sub = pack_pairs(state['pairs'][:k])
+    alphabet = np.unique(sub[0])
+    codes = np.zeros(256, dtype=np.uint8)
+    codes[alphabet] = np.arange(alphabet.size, dtype=np.uint8)
+    dense = codes[sub[0]]
+    vowels = set(b'aeiouy')
+    tab = np.array([[8 if a == b else (-2 if (a in vowels) == (b in vowels) else -4) for b in alphabet.tolist()]
+                    for a in alphabet.tolist()], dtype=np.int32)
+    res = {}
+    for name, sc, sym in (('equality', ctx.make_scoring(*DEFAULT_PARAMS), sub[0]),
+                          ('callable', ctx.make_scoring(0, 0, -7, -7, -3, 0, -1, subst=tab), dense)):
+        ctx.prepare(sym, *sub[1:], sc)
+        for _ in range(2):
+            ctx.run()
+        ctx.sync()
+        best = 1e9
+        for _ in range(4):
+            ctx.run()
+            ctx.sync()
+            best = min(best, ctx.timing()['kernel_ms'])
+        res[name] = best
+    c2 = int((sub[2].astype(np.int64) * sub[4]).sum())
+    out['callable_scorer'] = dict(pages=k, table_side=int(alphabet.size), equality_ms=res['equality'], callable_ms=res['callable'],
+                                  value=c2 / (res['callable'] * 1e-3) / 1e9, unit='GCUPS',
+                                  slowdown=res['callable'] / res['equality'],
+                                  what='textSeqCompare.py:27-29 over %d c2 pages: one launch, K x K table in shared memory' % k)
+    return out
+
+
 def consumer_leg(h):
     """The consumer either side of the path: object path vs array path."""
     from text_alignment_b200 import alignToOCR as atocr, latinSyllabification as latsyl, synth
@@ -774,6 +833,13 @@ def main():
         except Exception as e:                       # noqa: BLE001  (a side leg must not cost the headline line)
             consumer = dict(error=repr(e))
 
+    extras = None
+    if rank == 0 and args.workload == 'c2' and not args.no_others:
+        try:
+            extras = extras_leg(h, state)
+        except Exception as e:                       # noqa: BLE001
+            extras = dict(error=repr(e))
+
     # ---- the other BASELINE configs, short legs ------------------------------------------------------
     others = None
     if not args.no_others:
@@ -850,6 +916,8 @@ def main():
             line['python_list_shim'] = shim
         if consumer:
             line['consumer'] = consumer
+        if extras:
+            line['extras'] = extras
         if others is not None:
             line['others'] = others
         if sharded is not None:
