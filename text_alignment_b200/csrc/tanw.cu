@@ -107,10 +107,11 @@ struct LongPair {
 struct tanw_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_k3 = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_k3 = nullptr, s_l0 = nullptr, s_l1 = nullptr, s_out = nullptr;
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr,
                 ev_d2h0 = nullptr, ev_d2h1 = nullptr, ev_tab = nullptr, ev_survey = nullptr, ev_idle = nullptr;
-    cudaEvent_t ev_piece[kPieces] = {}, ev_chunk[kMaxChunks] = {}, ev_fork[kMaxChunks] = {}, ev_pages[kMaxChunks] = {};
+    cudaEvent_t ev_piece[kPieces] = {}, ev_chunk[kMaxChunks] = {}, ev_fork[kMaxChunks] = {}, ev_pages[kMaxChunks] = {},
+                ev_lines[kMaxChunks] = {};
     std::string err;
     int64_t arena_limit = 0;
     int64_t max_nm = 0;                   // largest n+m of the prepared batch (range check on rescore)
@@ -129,6 +130,8 @@ struct tanw_ctx {
     bool packed_ops = false;              // fetch delivers 2-bit packed op strings (tanw_set_packed_ops)
     bool batch_packed = false;            // ... as the prepared batch was laid out
     bool alternate = false;               // page kernels of successive chunks on s_k2 / s_k3, arenas of their own
+    bool alt_lines = false;               // line kernels of successive chunks on s_l0 / s_l1, arenas of their own
+    int64_t line_arena_bytes = 0;         // one line arena
     int64_t page_slots = 0;               // warp slots of one page arena
     int line16_max_n = 0;                 // tallest pair of the prepared batch on the 16-bit line kernel (0: none)
     int long_capacity = 0;                // resident warps for a cooperative launch
@@ -611,6 +614,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     int S = 1;
     int per = n_slices;                                  // slices per chunk
     bool alternate = false;                              // page kernels of successive chunks on two streams
+    bool alt_lines = false;                              // ... and the line kernels
     if (in.pipelined && n_slices > 1 && ctx->longs.empty() && !sc->subst) {
         const double copy_ms = (double)(sym_bytes_total + cap_total) / 45e6;
         const int64_t page_warps = (int64_t)ctx->sm_count * ctx->occ_plain * kWarpsPerBlock;
@@ -618,13 +622,14 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
             // Lines (with the odd page among them): chunks pay when the copies are long next to what
             // a chunk boundary costs (a few small launches), and a chunk should be whole rounds of
             // the line kernel's resident warps (eight pairs each).
-            const double want = std::sqrt(copy_ms / 0.03);
+            const double want = std::sqrt(copy_ms / 0.012);     // (successive chunks' line kernels overlap: a boundary is cheap)
             while (S * 2 <= std::min<int>(n_slices, kMaxChunks) && S * 2 <= want) S *= 2;
             if (S > 1) {
                 const double per_round = (double)ctx->sm_count * ctx->occ_line16 * kWarpsPerBlock * 8 / (double)slice_pairs;
                 const double rounds = std::max(1.0, std::floor((double)n_slices / S / per_round + 0.5));
                 per = (int)std::max(1.0, std::floor(rounds * per_round));
                 if ((n_slices + per - 1) / per > kMaxChunks) per = (n_slices + kMaxChunks - 1) / kMaxChunks;
+                alt_lines = true;
             }
         } else if (n_line_total == 0 && n_page_total >= 3 * page_warps && copy_ms > 0.02 * (double)cells / 1.6e9) {
             // Pages: two chunks whose kernels run on two streams with pointer arenas of their own,
@@ -704,6 +709,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     if (alternate && 2 * slots * slot_bytes > limit) alternate = false;       // one arena: the chunks' page kernels share a stream
     ctx->alternate = alternate;
     const int arenas = alternate ? 2 : 1;
+    if (S == 1) alt_lines = false;
     int line_grid = ctx->sm_count * ctx->occ_line;
     if (((int64_t)max_quads + kWarpsPerBlock - 1) / kWarpsPerBlock < line_grid)
         line_grid = (int)std::max<int64_t>(((int64_t)max_quads + kWarpsPerBlock - 1) / kWarpsPerBlock, 1);
@@ -723,6 +729,8 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->line16_slot = line16_slot;
     ctx->line16_max_n = n_line16_total > 0 ? std::max(max_nm16, 1) : 0;     // the tallest pair routed to the 16-bit kernel
     if (max_octets) line_arena = std::max(line_arena, (int64_t)line16_grid * kWarpsPerBlock * 8 * line16_slot);
+    line_arena = (line_arena + 255) / 256 * 256;
+    if (alt_lines && arenas * slots * slot_bytes + 2 * line_arena > limit) alt_lines = false;
     const int bnd_rows = max_n + 4;      // bnd[1..n] plus the prefetch overrun
 
     if (ctx->d_pairs.reserve(sizeof(PairDesc) * Pz) != cudaSuccess ||
@@ -732,7 +740,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         ctx->d_hist.reserve(sizeof(int) * (size_t)kHistStride * (size_t)S) != cudaSuccess ||
         ctx->d_classes.reserve(sizeof(LineClasses) * 2 * kMaxChunks) != cudaSuccess ||
         ctx->d_counter.reserve(sizeof(unsigned) * 4 * kMaxChunks) != cudaSuccess ||
-        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(arenas * slots * slot_bytes + line_arena, max_long), 256)) != cudaSuccess ||
+        ctx->d_arena.reserve((size_t)std::max<int64_t>(std::max(arenas * slots * slot_bytes + (alt_lines ? 2 : 1) * line_arena, max_long), 256)) != cudaSuccess ||
         ctx->d_bnd.reserve(sizeof(int2) * (size_t)std::max<int64_t>(arenas * slots * bnd_rows, 1)) != cudaSuccess ||
         reserve_zeroed(ctx, ctx->d_chain, sizeof(int4) * (size_t)max_long_bnd) != cudaSuccess ||
         ctx->d_ck.reserve(sizeof(int) * (size_t)(4 + max_ck)) != cudaSuccess ||
@@ -822,6 +830,8 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     la.pairs = a.pairs;
     la.ptr_arena = a.ptr_arena + (size_t)(arenas * slots * slot_bytes);        // behind the page kernel's slots
     ctx->page_slots = slots;
+    ctx->alt_lines = alt_lines;
+    ctx->line_arena_bytes = (line_arena + 255) / 256 * 256;
     la.slot_bytes = line_slot;
     la.ops = a.ops;
     la.ops_len = a.ops_len;
@@ -851,38 +861,47 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
     int launches = 0;
     TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned) * 4 * kMaxChunks, ctx->s_k));
     TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_misc.p, 0, sizeof(int), ctx->s_k));
-    bool cp_forked[kMaxChunks] = {};
+    bool cp_forked[kMaxChunks] = {}, cp_lines[kMaxChunks] = {};
     for (int c = 0; c < ctx->n_chunks; ++c) {
         if (int rc = build_chunk_tables(ctx, c)) return rc;
         const ChunkPlan &cp = ctx->chunk[c];
-        if (pipelined) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_piece[cp.piece], 0));
-        const bool forked = cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0 || ctx->alternate);
-        if (forked) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_fork[c], ctx->s_k));
+        const bool has_lines = cp.n_octets > 0 || cp.n_quads > 0;
+        const bool forked = cp.n_page > 0 && (has_lines || ctx->alternate);
+        const bool lines_away = ctx->alt_lines && has_lines;         // the chunk's line kernels leave s_k
+        const int lpar = lines_away ? (c & 1) : 0;
+        cudaStream_t ls = lines_away ? (lpar ? ctx->s_l1 : ctx->s_l0) : ctx->s_k;
+        if (forked || lines_away) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_fork[c], ctx->s_k));
+        if (lines_away) TANW_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->ev_fork[c], 0));
+        if (pipelined && (has_lines || !forked)) TANW_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->ev_piece[cp.piece], 0));
         if (cp.n_octets > 0) {
             LineArgs la = ctx->largs;
+            la.ptr_arena += (size_t)lpar * (size_t)ctx->line_arena_bytes;
             la.sorted = (const int *)ctx->d_lsorted.p + cp.first;
             la.classes = (const LineClasses *)ctx->d_classes.p + 2 * c;
             la.counter = (unsigned *)ctx->d_counter.p + 4 * c + 2;
             la.slot_bytes = ctx->line16_slot;
             la.n_quads = cp.n_octets;
             const int grid = (int)std::min<int64_t>(ctx->line16_grid, ((int64_t)cp.n_octets + kWarpsPerBlock - 1) / kWarpsPerBlock);
-            TANW_CUDA(ctx, launch_lines16(la, ctx->kp, ctx->var, std::max(grid, 1), ctx->s_k));
+            TANW_CUDA(ctx, launch_lines16(la, ctx->kp, ctx->var, std::max(grid, 1), ls));
             ++launches;
         }
         if (cp.n_quads > 0) {
             LineArgs la = ctx->largs;
+            la.ptr_arena += (size_t)lpar * (size_t)ctx->line_arena_bytes;
             la.sorted = (const int *)ctx->d_lsorted.p + cp.first;
             la.classes = (const LineClasses *)ctx->d_classes.p + 2 * c + 1;
             la.counter = (unsigned *)ctx->d_counter.p + 4 * c + 1;
             la.n_quads = cp.n_quads;
             const int grid = (int)std::min<int64_t>(ctx->line_grid, ((int64_t)cp.n_quads + kWarpsPerBlock - 1) / kWarpsPerBlock);
-            TANW_CUDA(ctx, launch_lines(la, ctx->kp, ctx->var, ctx->use_subst, std::max(grid, 1), ctx->s_k));
+            TANW_CUDA(ctx, launch_lines(la, ctx->kp, ctx->var, ctx->use_subst, std::max(grid, 1), ls));
             ++launches;
         }
-        if (ctx->batch_packed && (cp.n_octets > 0 || cp.n_quads > 0)) {
-            if (int rc = pack_chunk(ctx, cp, (1u << kRouteLine) | (1u << kRouteLine16), ctx->s_k)) return rc;
+        if (ctx->batch_packed && has_lines) {
+            if (int rc = pack_chunk(ctx, cp, (1u << kRouteLine) | (1u << kRouteLine16), ls)) return rc;
             ++launches;
         }
+        if (lines_away) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_lines[c], ls));
+        cp_lines[c] = lines_away;
         if (cp.n_page > 0) {
             BatchArgs a = ctx->args;
             a.order = (const int *)ctx->d_order.p + cp.first;
@@ -894,6 +913,7 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             a.ptr_arena += (size_t)parity * (size_t)(ctx->page_slots * ctx->slot_bytes);
             a.bnd_arena += (size_t)parity * (size_t)(ctx->page_slots * a.bnd_rows);
             if (forked) TANW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork[c], 0));
+            if (forked && pipelined) TANW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_piece[cp.piece], 0));
             TANW_CUDA(ctx, launch_pairs(a, ctx->kp, ctx->var, ctx->use_subst, ctx->batch_sym_bytes, ctx->multi,
                                         std::max(grid, 1), st));
             ++launches;
@@ -909,6 +929,8 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             // stream the caller sees (tanw_stream_handle) covers all of the batch's work
             for (int j = 0; j <= c; ++j)
                 if (cp_forked[j]) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_pages[j], 0));
+            for (int j = 0; j <= c; ++j)
+                if (cp_lines[j]) TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_lines[j], 0));
             for (const LongPair &lp : ctx->longs) {
                 const KParams kp = ctx->multi ? ctx->h_kparams[lp.sidx] : ctx->kp;
                 int rc = run_long_pair(ctx, lp, kp, ctx->var, &launches);
@@ -966,6 +988,8 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
         TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_chunk[c], 0));
         if (cp.n_page > 0 && (cp.n_octets > 0 || cp.n_quads > 0 || ctx->alternate))
             TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_pages[c], 0));
+        if (ctx->alt_lines && (cp.n_octets > 0 || cp.n_quads > 0))
+            TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_lines[c], 0));
         if (c == 0) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h0, ctx->s_out));
         if (packed && cp.count > 0) {
             const int64_t lo = (cp.ops_base >> 2) + cp.first, hi = ((cp.ops_base + cp.cap) >> 2) + cp.first + cp.count;
@@ -1092,7 +1116,7 @@ int tanw_create(int device, tanw_ctx **out)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     DeviceGuard guard(device);
     cudaError_t e = guard.err;
-    cudaStream_t *streams[] = { &ctx->s_in, &ctx->s_k, &ctx->s_k2, &ctx->s_k3, &ctx->s_out };
+    cudaStream_t *streams[] = { &ctx->s_in, &ctx->s_k, &ctx->s_k2, &ctx->s_k3, &ctx->s_l0, &ctx->s_l1, &ctx->s_out };
     for (auto s : streams)
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     cudaEvent_t *evs[] = { &ctx->ev_h2d0, &ctx->ev_h2d1, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_d2h0, &ctx->ev_d2h1 };
@@ -1107,6 +1131,7 @@ int tanw_create(int device, tanw_ctx **out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pages[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lines[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_survey, sizeof(Survey));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_misc, 256);
@@ -1136,7 +1161,7 @@ int tanw_destroy(tanw_ctx *ctx)
 {
     if (!ctx) return TANW_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t streams[] = { ctx->s_in, ctx->s_k, ctx->s_k2, ctx->s_k3, ctx->s_out };
+    cudaStream_t streams[] = { ctx->s_in, ctx->s_k, ctx->s_k2, ctx->s_k3, ctx->s_l0, ctx->s_l1, ctx->s_out };
     for (auto s : streams)
         if (s) cudaStreamSynchronize(s);
     DevBuf *bufs[] = { &ctx->d_sym, &ctx->d_n, &ctx->d_m, &ctx->d_toff, &ctx->d_ooff, &ctx->d_pairs, &ctx->d_route,
@@ -1155,6 +1180,8 @@ int tanw_destroy(tanw_ctx *ctx)
     for (auto ev : ctx->ev_fork)
         if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_pages)
+        if (ev) cudaEventDestroy(ev);
+    for (auto ev : ctx->ev_lines)
         if (ev) cudaEventDestroy(ev);
     if (ctx->h_survey) cudaFreeHost(ctx->h_survey);
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
@@ -1235,6 +1262,8 @@ int tanw_sync(tanw_ctx *ctx)
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k2));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k3));
+    TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_l0));
+    TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_l1));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return TANW_OK;
 }
