@@ -826,3 +826,27 @@ def test_packed_ops_are_the_same_alignments(oracle):
     finally:
         ctx.close()
     _ = oracle
+
+
+def test_callable_scorer_profile_and_lookup_paths(tsc, oracle):
+    """A tabulated scorer runs the page kernel on a per-lane query profile (signed bytes) when the
+    alphabet has at most 32 symbols and |score| <= 127, and on table lookups otherwise: both
+    against the oracle, with remainder passes of every strip width."""
+    def small(a, b):
+        return 7 if a == b else (-1 if (a in 'aeiou') == (b in 'aeiou') else -6)
+
+    def big(a, b):
+        return 200 if a == b else -150
+    rng = random.Random(21)
+    pages = [synth.make_pair(800 + k, 200 + 37 * k, 150 + 61 * k, 3, 30) for k in range(8)]         # m = 150 .. 577
+    wide_alpha = [chr(0x61 + k) for k in range(26)] + [chr(0x3b1 + k) for k in range(20)]           # 46 symbols
+    wide = [([rng.choice(wide_alpha) for _ in range(180)], [rng.choice(wide_alpha) for _ in range(260)]) for _ in range(3)]
+    for fn, pairs in ((small, [(list(t), list(o)) for t, o in pages]), (big, [(list(t), list(o)) for t, o in pages[:4]]),
+                      (small, wide)):
+        for gaps in ([-7, -6, -3, -1], [-7, -7, -3, 0], [2, -6, -3, -1]):
+            system = [fn] + gaps
+            got = tsc.perform_alignment_batch(pairs, system, return_scores=True)
+            for (T, O), (tra, ocr, score) in zip(pairs, got):
+                want = oracle.perform_alignment(T, O, system, full=True)
+                assert (tra, ocr) == (want[0], want[1]), (fn.__name__, gaps)
+                assert tuple(score) == _end(want[2]['end'])

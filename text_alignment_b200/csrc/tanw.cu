@@ -151,6 +151,7 @@ struct tanw_ctx {
     ChunkPlan chunk[kMaxChunks];
     KParams kp;
     bool use_subst = false, multi = false;
+    int page_subst = 0;                   // how the page kernel scores: 0 equality, 1 table lookups, 2 query profile
     int var = 0;                          // recurrence variant of the batch (tanw_kernels.cuh)
     BatchArgs args;
     LineArgs largs;
@@ -674,6 +675,12 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     // ---- kernel parameters ------------------------------------------------------------------
     ctx->kp = make_kparams(sc);
     ctx->use_subst = !multi && sc->subst != nullptr;
+    ctx->page_subst = ctx->use_subst ? 1 : 0;
+    if (ctx->use_subst && sb == 1 && sc->subst_k <= kProfileMaxK) {
+        bool small = true;                                  // the profile holds signed bytes
+        for (int64_t i = 0; i < (int64_t)sc->subst_k * sc->subst_k && small; ++i) small = sc->subst[i] >= -127 && sc->subst[i] <= 127;
+        if (small) ctx->page_subst = 2;
+    }
     ctx->multi = multi;
     ctx->var = var;
     ctx->max_nm = sv.max_nm;
@@ -681,7 +688,8 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->batch_packed = ctx->packed_ops;
 
     // ---- launch geometry and scratch ----------------------------------------------------------
-    int occ = ctx->use_subst ? ctx->occ_subst : ctx->occ_plain;
+    int occ = ctx->page_subst == 2 ? std::max(1, pairs_blocks_per_sm_profile(sc->subst_k))
+            : ctx->use_subst ? ctx->occ_subst : ctx->occ_plain;
 #ifdef TANW_TUNING
     if (const char *e = getenv("TANW_PAGE_BLOCKS")) occ = std::max(1, std::min(occ, atoi(e)));   // tuning builds only
 #endif
@@ -914,7 +922,7 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             a.bnd_arena += (size_t)parity * (size_t)(ctx->page_slots * a.bnd_rows);
             if (forked) TANW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork[c], 0));
             if (forked && pipelined) TANW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_piece[cp.piece], 0));
-            TANW_CUDA(ctx, launch_pairs(a, ctx->kp, ctx->var, ctx->use_subst, ctx->batch_sym_bytes, ctx->multi,
+            TANW_CUDA(ctx, launch_pairs(a, ctx->kp, ctx->var, ctx->page_subst, ctx->batch_sym_bytes, ctx->multi,
                                         std::max(grid, 1), st));
             ++launches;
             if (ctx->batch_packed) {

@@ -57,6 +57,23 @@ struct KParams {
     const int *subst;        // device table, entry = (score<<6)|kTagM, or nullptr
 };
 
+// Query profile of a tabulated scorer (SUBST == 2, page kernel): before a pass, every lane
+// tabulates, for each of the K transcript symbols, the scores against its own C OCR columns as
+// C signed bytes -- 16 bytes per (symbol, lane) in shared memory, laid out [symbol][lane][16] so
+// that a row's scores come with ONE conflict-free 128-bit load.  Per cell that leaves a byte
+// extraction (PRMT, sign-extending) and one multiply-add  m2 = score * 64 + (dc | tag M): one alu
+// instruction like the equality scorer's compare, where the table lookup per cell (SUBST == 1)
+// needs address arithmetic and a shared-memory load whose bank conflicts saturate the LSU
+// (measured on 2 000 config-2 pages, K = 24: 1.54 x the equality scorer's time).  Needs
+// K <= kProfileMaxK and |score| <= 127 (the host checks; else SUBST == 1).
+constexpr int kProfileMaxK = 32;
+__host__ __device__ inline int profile_bytes_per_warp(int k)
+{
+    const int tile = ((64 + 1) * 17 * 4 + 255) / 256 * 256;      // the traceback tile shares the space
+    const int prof = k * 32 * 16;
+    return prof > tile ? prof : tile;
+}
+
 struct PairDesc {
     long long t_off, o_off;  // into the symbol buffer
     long long ops_off;       // into the device op buffer (capacity n+m)
@@ -120,7 +137,7 @@ __device__ __forceinline__ int clean_tag_or(int v, int tag)
 
 // Symbol codes index the K x K table of a tabulated scorer: a code >= K (which the host reports as
 // an error after the batch) must not read outside the table.
-template <bool SUBST>
+template <int SUBST>
 __device__ __forceinline__ int table_code(int v, const KParams &kp)
 {
     return SUBST ? min(v, kp.subst_k - 1) : v;
@@ -155,16 +172,21 @@ struct Strip {
 //   xe, cx     : ex*i and ox - ex*i for this lane's row i
 // Returns the strip's right edge in q_out / y_out and the C pointer bytes in pw[C/4].
 // EYZ: gap_extend_y == 0 (the reference's default_sys), which saves the Y + ey add.
-template <int C, bool FINAL, bool SUBST, int VAR>
+template <int C, bool FINAL, int SUBST, int VAR>
 __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tch, int xe, int cx,
                                           int q_in, int y_in, int dul_in,
                                           int &q_out, int &y_out, unsigned (&pw)[C / 4],
-                                          int kfin, int (&cap)[3])
+                                          int kfin, int (&cap)[3], const uint4 *prof = nullptr)
 {
     constexpr bool FAST = (VAR >= 1);                 // X from D: no W
     constexpr bool YQ = (VAR == 0 || VAR >= 3);       // Y from Q = max(M, X); the edge carries (Q, Y)
     constexpr bool EYZ = (VAR == 2 || VAR == 4);
-    const int *srow = SUBST ? kp.subst + tch * kp.subst_k : nullptr;
+    const int *srow = SUBST == 1 ? kp.subst + tch * kp.subst_k : nullptr;
+    unsigned pr[4] = {0u, 0u, 0u, 0u};
+    if (SUBST == 2) {                                       // this row's scores against the strip's columns
+        const uint4 v = prof[tch * 32];
+        pr[0] = v.x; pr[1] = v.y; pr[2] = v.z; pr[3] = v.w;
+    }
     int q = q_in;                             // general: Q of the cell to the left; FAST: its D
     int ypl = EYZ ? y_in : y_in + kp.ey;      // Y of the column to the left, + ey
     int dul = dul_in;
@@ -172,9 +194,14 @@ __device__ __forceinline__ void strip_row(Strip<C> &s, const KParams &kp, int tc
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         // M[i][j] = max(M,X,Y)[i-1][j-1] + score, tagged as an M value         (:70-72)
-        const int dc = clean_tag(dul);
+        const int dc = SUBST == 2 ? clean_tag_or(dul, kTagM) : clean_tag(dul);
         int m2;
-        if (SUBST) {
+        if (SUBST == 2) {
+            int sx;                              // byte k & 3 of the profile word, sign-extended
+            const int b = k & 3;                 // selector: byte b, then its sign three times (an immediate once unrolled)
+            asm("prmt.b32 %0, %1, 0, %2;" : "=r"(sx) : "r"(pr[k >> 2]), "r"(b | ((b | 8) << 4) | ((b | 8) << 8) | ((b | 8) << 12)));
+            asm("mad.lo.s32 %0, %1, 64, %2;" : "=r"(m2) : "r"(sx), "r"(dc));
+        } else if (SUBST == 1) {
             m2 = dc + srow[s.oc[k]];            // generic load: the table is in shared memory when K <= kSubstSmemK
         } else {
             // compare + add + predicated add instead of compare + select + add: ptxas turns the
@@ -264,6 +291,7 @@ struct PassState {
     int2 *bw;              // &bnd[i+1]: where lane 31 leaves its right edge next
     uint8_t *pst;          // pointer bytes of this lane for the next step
     int c0;                // 0-based first column of the strip
+    const uint4 *prof;     // SUBST == 2: this lane's column of the warp's query profile
     int2 blk_cur;          // chained passes: current 8-row block of the left boundary, one row per lane 0..7
     int4 blk_raw;          // chained passes: the next block as loaded (stamps not yet checked)
 };
@@ -338,7 +366,7 @@ __device__ __forceinline__ int2 chain_take(const Chain &ch, int4 v, int base, in
 
 // One wavefront step of one pass.  GUARDED steps check whether the lane's row is inside
 // [1, n] (ramp-up / ramp-down) and capture the corner scores; steady steps do neither.
-template <int C, bool GUARDED, bool SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
+template <int C, bool GUARDED, int SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
 __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KParams &kp,
                                           int n, int t, int lane, bool has_next,
                                           int fin_lane, int fin_k, int (&cap)[3], const Chain &ch)
@@ -381,7 +409,7 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
         unsigned pw[C / 4];
         const int kfin = (GUARDED && i == n && lane == fin_lane) ? fin_k : -1;
         strip_row<C, GUARDED, SUBST, VAR>(s, kp, tch, ps.xe, ps.cx, q_in, y_in, dul_in,
-                                          ps.q_out, ps.y_out, pw, kfin, cap);
+                                          ps.q_out, ps.y_out, pw, kfin, cap, ps.prof);
         if (!CHAINED || ch.store) store_ptr_words<C>(ps.pst, pw);
         if (has_next && lane == 31) {
             if (CHAINED) st_volatile_v4(ch.out + i, make_int4(ps.q_out, ch.epoch, ps.y_out, ch.epoch));
@@ -423,12 +451,12 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
 //              bnd[i] with this pass's right edge 31 steps after lane 0 consumed it.
 //   ptr      : base of this pass's pointer bytes, laid out [step t][lane][C]
 //   fin_lane, fin_k : where column m lives in this pass (or fin_lane = -1)
-template <int C, bool SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
+template <int C, int SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
 __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restrict__ T,
                                           const SYM *__restrict__ O, int n, int m, int j0,
                                           bool has_next, const int2 *bnd, int2 *bnd_out,
                                           uint8_t *__restrict__ ptr, int fin_lane, int fin_k,
-                                          int (&cap)[3], const Chain &ch)
+                                          int (&cap)[3], const Chain &ch, uint4 *prof = nullptr)
 {
     const int lane = threadIdx.x & 31;
     const int c0 = j0 + lane * C;                 // 0-based first column of the strip
@@ -450,6 +478,20 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restri
         }
     }
     PassState ps;
+    ps.prof = nullptr;
+    if (SUBST == 2) {
+        // the query profile of this pass: scores of every transcript symbol against this lane's columns
+        for (int sym = 0; sym < kp.subst_k; ++sym) {
+            const int *row = kp.subst + sym * kp.subst_k;
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+                w[k >> 2] |= ((unsigned)(__ldg(row + s.oc[k]) >> kShift) & 0xFFu) << (8 * (k & 3));
+            prof[sym * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncwarp();
+        ps.prof = prof + lane;
+    }
     ps.c0 = c0;
     ps.q_out = (kp.bg * (c0 + C)) | kTagM;        // right edge of row 0
     ps.y_out = kNeg;
@@ -504,18 +546,18 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restri
         pass_step<C, true, SUBST, VAR, CHAINED, SYM>(s, ps, kp, n, t, lane, has_next, fin_lane, fin_k, cap, ch);
 }
 
-template <bool SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
+template <int SUBST, int VAR, bool CHAINED, typename SYM = uint8_t>
 __device__ __forceinline__ void dispatch_pass(int C, const KParams &kp, const SYM *T,
                                               const SYM *O, int n, int m, int j0,
                                               bool has_next, const int2 *bnd, int2 *bnd_out,
                                               uint8_t *ptr, int fin_lane, int fin_k, int (&cap)[3],
-                                              const Chain &ch)
+                                              const Chain &ch, uint4 *prof = nullptr)
 {
 #define TANW_CASE(CC)                                                                              \
     case CC:                                                                                       \
         if constexpr (CC <= kMaxC)                                                                 \
             fill_pass<CC, SUBST, VAR, CHAINED, SYM>(kp, T, O, n, m, j0, has_next, bnd, bnd_out, ptr, \
-                                                    fin_lane, fin_k, cap, ch);                      \
+                                                    fin_lane, fin_k, cap, ch, prof);                \
         break;
     switch (C) {
         TANW_CASE(4) TANW_CASE(8) TANW_CASE(12) TANW_CASE(16)
@@ -791,19 +833,24 @@ __device__ __forceinline__ KParams stage_subst(const KParams &kp, int *stab)
 // MULTI: every pair names its own scoring system (BatchArgs::kparams / sidx) -- the reference's
 // parameter sweep, 729 vectors over the same pages (evaluate_text_alignment.py:134-194), as ONE
 // launch; VAR is then the most general variant any system of the batch needs.
-template <bool SUBST, int VAR, typename SYM = uint8_t, bool MULTI = false>
+template <int SUBST, int VAR, typename SYM = uint8_t, bool MULTI = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp_launch)
 {
-    __shared__ unsigned tiles[kWarpsPerBlock][(kTileRows + 1) * kTileStride];
-    __shared__ int stab[SUBST ? kSubstSmemK * kSubstSmemK : 1];
+    // SUBST == 2: a warp's query profile and, after the fill, its traceback tile share one region
+    // of dynamic shared memory (profile_bytes_per_warp); otherwise the tiles are static
+    __shared__ unsigned tiles_static[SUBST == 2 ? 1 : kWarpsPerBlock][SUBST == 2 ? 1 : (kTileRows + 1) * kTileStride];
+    __shared__ int stab[SUBST == 1 ? kSubstSmemK * kSubstSmemK : 1];
+    extern __shared__ uint4 dyn_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * kWarpsPerBlock + warp;
     uint8_t *const ptr = a.ptr_arena + (size_t)slot * (size_t)a.slot_bytes;
     int2 *const bnd = a.bnd_arena + (size_t)slot * (size_t)a.bnd_rows;
     KParams kp = kp_launch;
-    if (SUBST) kp = stage_subst(kp_launch, stab);
+    if (SUBST == 1) kp = stage_subst(kp_launch, stab);
+    uint4 *const prof = SUBST == 2 ? dyn_smem + (size_t)warp * (profile_bytes_per_warp(kp_launch.subst_k) / 16) : nullptr;
+    unsigned *const tile = SUBST == 2 ? reinterpret_cast<unsigned *>(prof) : tiles_static[SUBST == 2 ? 0 : warp];
 
     for (;;) {
         unsigned idx = 0;
@@ -841,7 +888,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp_launch)
                 const int fin_k = last ? cc % C : -1;
                 dispatch_pass<SUBST, VAR, false, SYM>(C, kp, T, O, n, m, j0, !last, bnd, bnd,
                                                  ptr + (size_t)ps * (size_t)pass_bytes, fin_lane, fin_k, cap,
-                                                 no_chain());
+                                                 no_chain(), prof);
                 __syncwarp();
             }
             // the lane that owns column m holds the corner scores
@@ -852,7 +899,7 @@ align_pairs_kernel(const BatchArgs a, const __grid_constant__ KParams kp_launch)
         }
         __syncwarp();
         uint8_t *ops = a.ops + pd.ops_off;
-        const int L = traceback_warp(ptr, n, m, kMaxC, ops + (size_t)n + (size_t)m, tiles[warp], lane);
+        const int L = traceback_warp(ptr, n, m, kMaxC, ops + (size_t)n + (size_t)m, tile, lane);
         TANW_ASSERT(a.check, L >= max(n, m) && L <= n + m, 2);
         if (lane == 0) {
             a.ops_len[p] = L;
@@ -927,7 +974,7 @@ struct LineState {
     uint8_t *pst;
 };
 
-template <int C, bool GUARDED, bool SUBST, int VAR>
+template <int C, bool GUARDED, int SUBST, int VAR>
 __device__ __forceinline__ void line_step(Strip<C> &s, LineState &ls, const KParams &kp, int n, bool act,
                                           int t, int gl, int fin_lane, int fin_k, int (&cap)[3])
 {
@@ -1029,7 +1076,7 @@ __device__ __forceinline__ int traceback_groups(const uint8_t *ptr, int n, int m
     return __shfl_sync(kFull, k, 0, kLineG);
 }
 
-template <int C, bool SUBST, int VAR>
+template <int C, int SUBST, int VAR>
 __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, int p, uint8_t *ptr,
                                           unsigned *tile, int lane)
 {
@@ -1133,7 +1180,7 @@ __device__ __forceinline__ void line_quad(const LineArgs &a, const KParams &kp, 
     }
 }
 
-template <bool SUBST, int VAR>
+template <int SUBST, int VAR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
 align_lines_kernel(const LineArgs a, const __grid_constant__ KParams kp_launch)
 {
@@ -1193,7 +1240,7 @@ struct LongArgs {
     int *check;            // TANW_CHECKED builds: first failed device assertion
 };
 
-template <bool SUBST, int VAR, typename SYM = uint8_t>
+template <int SUBST, int VAR, typename SYM = uint8_t>
 __global__ void __launch_bounds__(32, 8)
 align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
 {

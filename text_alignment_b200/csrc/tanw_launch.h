@@ -3,16 +3,17 @@
 // builds in parallel; tanw.cu (the C ABI) only sees these functions.
 //
 // `var` is the recurrence variant (tanw_kernels.cuh: 0 general, 1 gap opens <= 0, 2 gap opens <= 0
-// and gap_extend_y == 0), `subst` a tabulated scorer, `sym_bytes` 1 or 2 (16-bit symbol codes run
+// and gap_extend_y == 0), `subst` a tabulated scorer (page kernel: 1 table lookups, 2 query profile), `sym_bytes` 1 or 2 (16-bit symbol codes run
 // the general variant only), `multi` per-pair scoring systems (uint8 symbols, equality scorer).
 #pragma once
 #include "tanw_kernels.cuh"
 
 namespace tanw {
 
-cudaError_t launch_pairs(const BatchArgs &a, const KParams &kp, int var, bool subst, int sym_bytes, bool multi,
+cudaError_t launch_pairs(const BatchArgs &a, const KParams &kp, int var, int subst, int sym_bytes, bool multi,
                          int grid, cudaStream_t stream);
 int pairs_blocks_per_sm(bool subst);
+int pairs_blocks_per_sm_profile(int subst_k);    // subst == 2: the query-profile form (K <= kProfileMaxK, |score| <= 127)
 
 cudaError_t launch_lines(const LineArgs &a, const KParams &kp, int var, bool subst, int grid, cudaStream_t stream);
 int lines_blocks_per_sm();

@@ -6,7 +6,7 @@
 
 namespace tanw {
 
-template <bool SUBST, int VAR>
+template <int SUBST, int VAR>
 static cudaError_t go(const LineArgs &a, const KParams &kp, int grid, cudaStream_t stream)
 {
     align_lines_kernel<SUBST, VAR><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, kp);
@@ -17,15 +17,15 @@ cudaError_t launch_lines(const LineArgs &a, const KParams &kp, int var, bool sub
 {
     if (subst) {
         switch (var) {
-        case 2:  return go<true, 2>(a, kp, grid, stream);
-        case 1:  return go<true, 1>(a, kp, grid, stream);
-        default: return go<true, 0>(a, kp, grid, stream);
+        case 2:  return go<1, 2>(a, kp, grid, stream);
+        case 1:  return go<1, 1>(a, kp, grid, stream);
+        default: return go<1, 0>(a, kp, grid, stream);
         }
     }
     switch (var) {
-    case 2:  return go<false, 2>(a, kp, grid, stream);
-    case 1:  return go<false, 1>(a, kp, grid, stream);
-    default: return go<false, 0>(a, kp, grid, stream);
+    case 2:  return go<0, 2>(a, kp, grid, stream);
+    case 1:  return go<0, 1>(a, kp, grid, stream);
+    default: return go<0, 0>(a, kp, grid, stream);
     }
 }
 
@@ -49,7 +49,7 @@ int lines16_blocks_per_sm()
 int lines_blocks_per_sm()
 {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_lines_kernel<true, 0>, kWarpsPerBlock * 32, 0) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_lines_kernel<1, 0>, kWarpsPerBlock * 32, 0) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }

@@ -59,19 +59,19 @@ trace_long_kernel(const uint8_t *ptr, const PairDesc *pd, int cfull, int r0, int
 const void *long_kernel(int var, bool subst, int sym_bytes)
 {
     if (sym_bytes == 2)
-        return subst ? (const void *)align_long_kernel<true, 0, uint16_t> : (const void *)align_long_kernel<false, 0, uint16_t>;
-    if (subst) return (const void *)align_long_kernel<true, 0, uint8_t>;
+        return subst ? (const void *)align_long_kernel<1, 0, uint16_t> : (const void *)align_long_kernel<0, 0, uint16_t>;
+    if (subst) return (const void *)align_long_kernel<1, 0, uint8_t>;
     // variants 3 / 4: the recurrences of 1 / 2 with the shorter dependent chain along a row
     // (config 5: fill 16.34 -> 16.11 ms)
-    return var == 2 ? (const void *)align_long_kernel<false, 4, uint8_t>
-         : var == 1 ? (const void *)align_long_kernel<false, 3, uint8_t>
-                    : (const void *)align_long_kernel<false, 0, uint8_t>;
+    return var == 2 ? (const void *)align_long_kernel<0, 4, uint8_t>
+         : var == 1 ? (const void *)align_long_kernel<0, 3, uint8_t>
+                    : (const void *)align_long_kernel<0, 0, uint8_t>;
 }
 
 int long_blocks_per_sm()
 {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_long_kernel<true, 0, uint8_t>, 32, 0) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_long_kernel<1, 0, uint8_t>, 32, 0) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
