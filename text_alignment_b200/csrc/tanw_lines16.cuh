@@ -29,7 +29,10 @@
 #define TANW_L16_ROWS 8
 #endif
 #ifndef TANW_L16_STREAM
-#define TANW_L16_STREAM 1
+#define TANW_L16_STREAM 2
+#endif
+#ifndef TANW_L16_LDPOL
+#define TANW_L16_LDPOL 1
 #endif
 #ifndef TANW_L16_PREFETCH
 #define TANW_L16_PREFETCH 1
@@ -147,6 +150,50 @@ struct Line16State {
     uint8_t *pstA, *pstB;
 };
 
+// Pointer words of a row: TANW_L16_STREAM 0 = st.cg, 1 = st.cs (evict first), 2 = L2 evict-last hint.
+template <int C>
+__device__ __forceinline__ void l16_store_ptr(uint8_t *dst, const unsigned (&pw)[C / 4])
+{
+#if TANW_L16_STREAM == 2
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    if (C % 16 == 0) {
+#pragma unroll
+        for (int v = 0; v < C / 16; ++v)
+            asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
+                         :: "l"(dst + 16 * v), "r"(pw[4 * v]), "r"(pw[4 * v + 1]), "r"(pw[4 * v + 2]), "r"(pw[4 * v + 3]), "l"(pol) : "memory");
+    } else if (C % 8 == 0) {
+#pragma unroll
+        for (int v = 0; v < C / 8; ++v)
+            asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;"
+                         :: "l"(dst + 8 * v), "r"(pw[2 * v]), "r"(pw[2 * v + 1]), "l"(pol) : "memory");
+    } else {
+#pragma unroll
+        for (int v = 0; v < C / 4; ++v)
+            asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(dst + 4 * v), "r"(pw[v]), "l"(pol) : "memory");
+    }
+#else
+    store_ptr_words<C, TANW_L16_STREAM != 0>(dst, pw);
+#endif
+}
+
+// Pointer word read back by the traceback: TANW_L16_LDPOL 0 = ld.cg, 1 = L2 evict-first hint (the
+// line is dead once the walk has passed it), 2 = ld.lu.
+__device__ __forceinline__ unsigned l16_ld(const unsigned *p)
+{
+#if TANW_L16_LDPOL == 1
+    unsigned long long pol;
+    unsigned v;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#elif TANW_L16_LDPOL == 2
+    return __ldlu(p);
+#else
+    return __ldcg(p);
+#endif
+}
+
 template <int C, bool GUARDED, bool EYZ>
 __device__ __forceinline__ void line_step16(Strip16<C> &s, Line16State &ls, const K16 &kp, int nA, int nB,
                                             bool actA, bool actB, int t, int gl,
@@ -173,8 +220,8 @@ __device__ __forceinline__ void line_step16(Strip16<C> &s, Line16State &ls, cons
         const int kfinB = (GUARDED && rowB && i == nB && gl == finB_lane) ? finB_k : -1;
         strip_row16<C, GUARDED, EYZ>(s, kp, tch2, pk_add(ls.xe), pk_simd(kp.ox - ls.xe), q_in, y_in, dul_in,
                                      ls.q_out, ls.y_out, pwA, pwB, kfinA, kfinB, cap);
-        if (!GUARDED || rowA) store_ptr_words<C, TANW_L16_STREAM != 0>(ls.pstA, pwA);
-        if (!GUARDED || rowB) store_ptr_words<C, TANW_L16_STREAM != 0>(ls.pstB, pwB);
+        if (!GUARDED || rowA) l16_store_ptr<C>(ls.pstA, pwA);
+        if (!GUARDED || rowB) l16_store_ptr<C>(ls.pstB, pwB);
     }
     ls.q_prev = q_in;
     ls.xe += kp.ex;
@@ -197,6 +244,11 @@ __device__ __forceinline__ void line_step16(Strip16<C> &s, Line16State &ls, cons
 //     the L2 by then (1.25 GB per launch) take 0.36 ms -- DRAM-bound on random 32-byte reads;
 //   * the same with a strip-major pointer layout (consecutive rows of a strip share sectors; the
 //     walk then needs 0.28 ms) makes the fill's stores uncoalesced: fill 1.56 ms.
+// The tile loads miss the L2 although a warp reads what it wrote tens of microseconds before: a
+// config-3 octet holds 72 KB of pointer bytes and 2 368 resident warps keep ~100 MB of them alive,
+// more than the L2 retains beside the rest of the traffic (ncu: 1.13 GB written, 0.93 GB read
+// back from DRAM per launch whatever the store flavour).  Marking the stores evict-last and the
+// read-backs evict-first (a line is dead once the walk has passed it) gains 2 % (0.794 -> 0.777 ms).
 constexpr int kL16Rows = TANW_L16_ROWS;                // rows of a traceback tile: 8 or 16
 constexpr int kL16PerLane = kL16Rows / kLineG;         // tile rows a lane loads
 constexpr int kL16TileWords = (kL16Rows + 1) * kLineTile;
@@ -213,11 +265,11 @@ __device__ __forceinline__ void l16_load(const uint8_t *ptr, bool mine, int hx, 
         if (mine && row >= 1) {
             const unsigned *hi = reinterpret_cast<const unsigned *>(ptr + ((size_t)(row + sidx) * kLineG + sidx) * C);
 #pragma unroll
-            for (int q = 0; q < C / 4; ++q) w[rr][C / 4 + q] = __ldcg(hi + q);
+            for (int q = 0; q < C / 4; ++q) w[rr][C / 4 + q] = l16_ld(hi + q);
             if (sidx >= 1) {
                 const unsigned *lo = reinterpret_cast<const unsigned *>(ptr + ((size_t)(row + sidx - 1) * kLineG + sidx - 1) * C);
 #pragma unroll
-                for (int q = 0; q < C / 4; ++q) w[rr][q] = __ldcg(lo + q);
+                for (int q = 0; q < C / 4; ++q) w[rr][q] = l16_ld(lo + q);
             }
         }
     }
