@@ -293,7 +293,6 @@ struct PassState {
     int c0;                // 0-based first column of the strip
     const uint4 *prof;     // SUBST == 2: this lane's column of the warp's query profile
     int2 blk_cur;          // chained passes: current 8-row block of the left boundary, one row per lane 0..7
-    int4 blk_raw;          // chained passes: the next block as loaded (stamps not yet checked)
 };
 
 // Chained passes (one huge pair spread over many warps): stripe w leaves its right edge in
@@ -314,12 +313,13 @@ struct Chain {
     int m;                 // columns = stride of the checkpoint arrays
     bool store;            // write pointer bytes (false in the forward checkpointing sweep)
     int *check;            // TANW_CHECKED builds: first failed device assertion
+    int4 *stage;           // shared memory: kChainBlock records, where the next block of `in` lands
 };
 __device__ __forceinline__ Chain no_chain()
 {
     Chain c;
     c.in = nullptr; c.out = nullptr; c.epoch = 0;
-    c.r0 = 0; c.ck_in = nullptr; c.ck_out = nullptr; c.m = 0; c.store = true; c.check = nullptr;
+    c.r0 = 0; c.ck_in = nullptr; c.ck_out = nullptr; c.m = 0; c.store = true; c.check = nullptr; c.stage = nullptr;
     return c;
 }
 constexpr int kChainBlock = 8;         // boundary rows fetched per coalesced load (lanes 0..7)
@@ -337,18 +337,30 @@ __device__ __forceinline__ void st_volatile_v4(int4 *p, int4 v)
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // Rows base .. base+7 of the left stripe's edge, one per lane 0..7.  chain_issue only starts the
-// load; chain_take, called a block (8 steps) later, checks the stamps and spins only if the
+// copy; chain_take, called a block (8 steps) later, checks the stamps and spins only if the
 // producer has not got there yet -- so the L2 round trip overlaps the 8 steps in between
-// (ncu: with a blocking fetch a stripe spent a third of its time in this load).
-__device__ __forceinline__ int4 chain_issue(const Chain &ch, int base, int n, int lane)
+// (ncu: with a blocking fetch a stripe spent a third of its time in this load).  The copy is an
+// asynchronous one into shared memory (LDGSTS) rather than a load into registers: ptxas puts every
+// global load of the loop on one scoreboard, so the per-step transcript byte -- an L1 hit -- waited
+// for the far-L2 round trip of a block fetch issued just before it (18 % of a stripe's time).
+__device__ __forceinline__ void chain_issue(const Chain &ch, int base, int n, int lane)
 {
-    int4 v = make_int4(0, ch.epoch, 0, ch.epoch);
-    if (lane < kChainBlock && base + lane <= n) v = ld_volatile_v4(ch.in + base + lane);
-    return v;
+    if (lane < kChainBlock && base + lane <= n) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ch.stage + lane);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(ch.in + base + lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ int2 chain_take(const Chain &ch, int4 v, int base, int n, int lane)
+__device__ __forceinline__ int2 chain_take(const Chain &ch, int base, int n, int lane)
 {
     const bool mine = lane < kChainBlock && base + lane <= n;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    int4 v = make_int4(0, ch.epoch, 0, ch.epoch);
+    if (mine) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(ch.stage + lane);
+        asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src) : "memory");
+    }
 #ifdef TANW_CHECKED
     const long long t0 = clock64();
 #endif
@@ -385,8 +397,8 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
             const int r = t + 1;                          // boundary row needed by the next step
             const int j = (r - 1) & (kChainBlock - 1);
             if (j == 0) {                         // rows r .. r+7 were requested 8 steps ago
-                ps.blk_cur = chain_take(ch, ps.blk_raw, r, n, lane);
-                if (r + kChainBlock <= n) ps.blk_raw = chain_issue(ch, r + kChainBlock, n, lane);
+                ps.blk_cur = chain_take(ch, r, n, lane);
+                if (r + kChainBlock <= n) chain_issue(ch, r + kChainBlock, n, lane);
             }
             ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, j);
             ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, j);
@@ -502,10 +514,10 @@ __device__ __forceinline__ void fill_pass(const KParams &kp, const SYM *__restri
         ps.q_prev = (c0 == 0) ? ((kp.bg * ch.r0) | kTagM) : ((c0 - 1 < m) ? ch.ck_in[ch.m + c0 - 1] : 0);
     }
     ps.blk_cur = make_int2(0, 0);
-    ps.blk_raw = make_int4(0, 0, 0, 0);
     if (CHAINED) {
-        ps.blk_cur = chain_take(ch, chain_issue(ch, 1, n, lane), 1, n, lane);           // rows 1..8
-        if (1 + kChainBlock <= n) ps.blk_raw = chain_issue(ch, 1 + kChainBlock, n, lane);
+        chain_issue(ch, 1, n, lane);
+        ps.blk_cur = chain_take(ch, 1, n, lane);                                        // rows 1..8
+        if (1 + kChainBlock <= n) chain_issue(ch, 1 + kChainBlock, n, lane);
         ps.bnext.x = __shfl_sync(kFull, ps.blk_cur.x, 0);
         ps.bnext.y = __shfl_sync(kFull, ps.blk_cur.y, 0);
     } else {
@@ -1268,6 +1280,8 @@ align_long_kernel(const LongArgs a, const __grid_constant__ KParams kp)
     ch.m = m;
     ch.store = a.store != 0;
     ch.check = a.check;
+    __shared__ __align__(16) int4 chain_stage[kChainBlock];
+    ch.stage = chain_stage;
     // Launch-constant operands of the steady loop, held in registers: left as kernel parameters
     // they are re-read from the constant bank (5 LDCU + 1 LDC at the top of every row) and the
     // row's dependent chain -- what bounds a stripe -- waits for them.  A round trip through shared
