@@ -651,12 +651,29 @@ constexpr int kTileStride = kTileWords + 1;        // words per tile row in shar
 // walker's own shared-memory loads.
 // Ops are written back to front at the END of the pair's op buffer (capacity n+m); x, y, st, k are
 // updated in every lane.  st = -1: take mat_ptr of the start cell first (:102).
+__device__ __forceinline__ unsigned lds_u8(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// 32 consecutive rows of one pointer word, going up from the row at p.
+template <int C>
+__device__ __forceinline__ void tile_rows(const uint8_t *p, unsigned (&w)[32])
+{
+#pragma unroll
+    for (int r = 0; r < 32; ++r) w[r] = __ldcg(reinterpret_cast<const unsigned *>(p - r * 32 * C));
+}
+
 __device__ __forceinline__ void traceback_core(const uint8_t *ptr, int n, int m, int cfull,
                                                uint8_t *ops_end, unsigned *tile, int lane,
                                                int &x, int &y, int &st, int &k)
 {
     const PtrMap map(n, m, cfull);
-    const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
+    // the tile's byte address in the shared window, taken once: left to the compiler, the walk loop
+    // re-derives it from the generic pointer in every iteration (S2UR + ULEA on its dependent chain)
+    const unsigned tb = (unsigned)__cvta_generic_to_shared(tile);
     while (x > 0 && y > 0) {
         // ---- tile load: word columns wq_hi-15 .. wq_hi, rows x .. x-63 ---------------------------
         const int wq_hi = (y - 1) >> 2;
@@ -664,37 +681,50 @@ __device__ __forceinline__ void traceback_core(const uint8_t *ptr, int n, int m,
         const int wq = wq_hi - (lane & 15);
         const int row_hi = x - 32 * (lane >> 4);             // its first row (it goes up from there)
         unsigned w[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) w[r] = 0u;
         if (wq >= 0) {
             PtrCursor cur;
             cur.seek(map, wq);
-            const uint8_t *base = ptr + cur.rowless;
-            const long long step = 32ll * cur.C;
+            const uint8_t *p = ptr + cur.at_row(row_hi);           // the word of row_hi; row - 1 is 32 * C bytes before
+            if (x >= kTileRows) {
+                // (warp-uniform) all 64 rows are inside the matrix: the strip width as a compile-time
+                // constant turns the 32 addresses into immediate offsets of one base register
+                // (the generic loop below spends ten instructions per load on 64-bit multiplies)
+                switch (cur.C) {
+                case 4:  tile_rows<4>(p, w); break;
+                case 8:  tile_rows<8>(p, w); break;
+                case 12: tile_rows<12>(p, w); break;
+                default: tile_rows<16>(p, w); break;
+                }
+            } else {
+                const int step = 32 * cur.C;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                w[r] = 0u;
-                if (row_hi - r >= 1) w[r] = __ldcg(reinterpret_cast<const unsigned *>(base + (long long)(row_hi - r) * step));
+                for (int r = 0; r < 32; ++r) {
+                    if (row_hi - r >= 1) w[r] = __ldcg(reinterpret_cast<const unsigned *>(p));
+                    p -= step;
+                }
             }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) w[r] = 0u;
         }
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 32; ++r) tile[(32 * (lane >> 4) + r) * kTileStride + q] = w[r];
         __syncwarp();
+        // (an L2 prefetch of the tile the walk will most likely enter next, issued here, changes
+        // nothing: 17.15 ms with and without on config 5 -- the tile phase is not DRAM latency)
         // ---- walk inside the tile, a run per iteration -----------------------------------------------
         // tile row R = matrix row x - R; tile byte column c = matrix column (col_lo + c + 1)
         const int col_lo = (wq_hi - (kTileWords - 1)) * 4;          // 0-based matrix column of tile byte 0
         const int rows_avail = min(x, kTileRows);
         const int c_min = max(0, -col_lo);                          // tile column of matrix column 1
         int R = 0, c = (y - 1) - col_lo;
-        if (st < 0) st = 2 - (int)(tb[c] & 3u);                                           // :102
+        if (st < 0) st = 2 - (int)(lds_u8(tb + c) & 3u);                                           // :102
         for (;;) {
             const int dx = (st != 2), dy = (st != 1);
             const int Rl = R + lane * dx, cl = c - lane * dy;
             const bool valid = Rl < rows_avail && cl >= c_min;
             int nxt = -1;
-            if (valid) nxt = 2 - (int)((tb[Rl * (kTileStride * 4) + cl] >> (2 * st)) & 3u);
+            if (valid) nxt = 2 - (int)((lds_u8(tb + Rl * (kTileStride * 4) + cl) >> (2 * st)) & 3u);
             const unsigned same = __ballot_sync(kFull, valid && nxt == st);
             const unsigned val = __ballot_sync(kFull, valid);
             const int run = (same == kFull) ? 32 : __ffs(~same) - 1; // leading lanes that stay in the state
