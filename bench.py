@@ -328,7 +328,7 @@ def run_reference(args):
                                   sample=sample_text(sample, whole, args.workload, kind_text)),
                 e2e=dict(value=gcups, unit='GCUPS', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -772,7 +772,27 @@ def consumer_leg(h):
                      '(CharBox objects + one regex per syllable, as the reference)')
 
 
+_json_out = [None]
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that chat on file descriptor 1 (NCCL prints
+    its version there) are sent to stderr, and emit() writes to the original descriptor."""
+    if _json_out[0] is None:
+        sys.stdout.flush()
+        _json_out[0] = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _json_out[0] or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -814,7 +834,7 @@ def main():
     c1 = time.perf_counter()
     clocks = sampler.stop(c0, c1)
     if frag is None:
-        print(json.dumps(dict(error='parity check against the oracle FAILED; no number reported')))
+        emit(dict(error='parity check against the oracle FAILED; no number reported'))
         return 2
 
     # ---- the Python list <-> buffer shim, reported separately (it is not the path) ----
@@ -860,7 +880,7 @@ def main():
             else:
                 f, _ = measure(h, which, WORKLOADS[which]['default_pairs'], 3, 3, min(args.parity_pairs, 64), full=False)
             if f is None:
-                print(json.dumps(dict(error='parity check against the oracle FAILED on %s; no number reported' % which)))
+                emit(dict(error='parity check against the oracle FAILED on %s; no number reported' % which))
                 return 2
             others[which] = dict(
                 workload=WORKLOADS[which]['name'], n_gpus=1 if solo else world, value=f['value'], unit='GCUPS',
@@ -930,7 +950,7 @@ def main():
             k_cells, k_wall, k = cpu_c_oracle(state['packed'], h.cores, max(h.cores * 4, 64))
             line['cpu_baseline_c'] = dict(value=k_cells / k_wall / 1e9, unit='GCUPS', cores=h.cores, kind='port',
                                           sample='%d full pages, oracle/nw_oracle.c (scalar C, float64), %d threads' % (k, h.cores))
-        print(json.dumps(line))
+        emit(line)
         if args.out:
             with open(args.out, 'w') as f:
                 json.dump(line, f, indent=1)
