@@ -5,7 +5,8 @@
 
 Each library runs in a process of its own (a process loads one libtanw).  Prints GCUPS and ms per
 launch, and checks the first 64 pairs against the C oracle.  Used to compare kernel variants
-built by `__graft_entry__.build_library(out, defines=[...])` within one gpurun call."""
+built by `__graft_entry__.build_library(out, defines=[...])` within one gpurun call.
+KB_PAIRS=<n> overrides the number of pairs (e.g. 1250: one GPU's share of config 2 over eight)."""
 import os
 import subprocess
 import sys
@@ -20,7 +21,7 @@ def one(workload, lib, steps=8):
     from text_alignment_b200 import _native
     if lib:
         _native.load(lib)
-    npairs = bench.WORKLOADS[workload]['default_pairs']
+    npairs = int(os.environ.get('KB_PAIRS', 0)) or bench.WORKLOADS[workload]['default_pairs']
     packed, pairs = bench.make_workload(workload, 0, npairs, 16)
     ctx = _native.Context(0)
     sc = ctx.make_scoring(*bench.DEFAULT_PARAMS)
