@@ -1,6 +1,6 @@
 // tools/int32_pipes.cu -- issue-rate micro-benchmarks of the integer instructions the NW
 // kernels are built from, on every SM.  Prints lane-ops per clock per SM for each.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o int32_pipes int32_pipes.cu && ./int32_pipes
+//   nvcc --cudart=shared -gencode arch=compute_100a,code=sm_100a -O3 -o int32_pipes int32_pipes.cu && ./int32_pipes
 // Each kernel runs 16 independent dependency chains per thread; operands live in registers
 // that ptxas cannot prove equal, so chains are not merged or hoisted (checked in the SASS).
 #include <cstdio>
