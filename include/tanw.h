@@ -177,6 +177,23 @@ int  tanw_align_batch_multi(tanw_ctx *ctx,
                             uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
                             int32_t *ops_len, int32_t *scores);
 
+/* One batch over several devices (pages are independent, alignToOCR.py:273 is one
+ * call per page -- the batch is partitioned, there is no exchange step).  Shard d = the pairs
+ * bounds[d] .. bounds[d+1]-1 (bounds[0] = 0, bounds[n_ctx] = n_pairs, non-decreasing; an empty
+ * shard is allowed) is aligned on ctxs[d] -- contexts of different devices, or several contexts of
+ * one device -- by one host thread per shard, and writes its op strings, lengths and scores
+ * straight into its slice of the caller's arrays: the gather is the layout itself.  All other
+ * arguments as tanw_align_batch for the WHOLE batch.  Returns the first shard's error, with its
+ * text in ctxs[0]'s tanw_last_error.  Not with tanw_set_packed_ops contexts.  The caller must
+ * not use any of the contexts from another thread during the call. */
+int  tanw_align_batch_sharded(tanw_ctx *const *ctxs, int32_t n_ctx, const int64_t *bounds,
+                              const uint8_t *symbols, int64_t symbols_len,
+                              const int64_t *t_off, const int32_t *n,
+                              const int64_t *o_off, const int32_t *m,
+                              int64_t n_pairs, const tanw_scoring *scoring,
+                              uint8_t *ops, const int64_t *ops_off, int64_t ops_capacity,
+                              int32_t *ops_len, int32_t *scores);
+
 /* ---- the same in three phases (bench.py times `run` alone with inputs resident in HBM) ------ */
 int  tanw_batch_prepare(tanw_ctx *ctx,
                         const uint8_t *symbols, int64_t symbols_len,

@@ -27,6 +27,51 @@ def test_two_devices_match_one_device():
         assert np.array_equal(one[0][one[1][k]:one[1][k] + one[2][k]], many[0][many[1][k]:many[1][k] + many[2][k]])
 
 
+def _batch(pairs):
+    buf = np.frombuffer(''.join(t + o for t, o in pairs).encode(), dtype=np.uint8)
+    n = np.array([len(t) for t, _ in pairs], dtype=np.int32)
+    m = np.array([len(o) for _, o in pairs], dtype=np.int32)
+    t_off = np.concatenate([[0], np.cumsum(n.astype(np.int64) + m)[:-1]]).astype(np.int64)
+    return buf, t_off, n, t_off + n, m
+
+
+def test_native_sharded_entry_bounds_and_errors():
+    """tanw_align_batch_sharded: arbitrary shard boundaries (empty shards, one pair per shard),
+    several contexts on one device, results in the caller's arrays; a shard's error comes back with
+    its shard named; a context listed twice or a packed-ops context is refused."""
+    from text_alignment_b200 import _native, textSeqCompare as tsc
+    pairs = [synth.c3_pair(k) for k in range(300)] + [synth.c2_pair(k) for k in range(5)] + [('', 'abc'), ('', '')]
+    buf, t_off, n, o_off, m = _batch(pairs)
+    params = (8, -4, -7, -7, -3, 0, -1)
+    P = len(pairs)
+    one = tsc.align_packed(buf, t_off, n, o_off, m, params, devices=[0])
+    ctxs = [tsc.get_context(0, replica=r) for r in range(3)]
+    for bounds in ([0, 0, 300, P], [0, 1, 2, P], [0, P, P, P], [0, 150, 303, P]):
+        ops_off, total = _native.Context.canonical_ops_layout(n, m)
+        out = (np.full(total + 7, 9, np.uint8), np.zeros(P, np.int32), np.zeros((P, 3), np.int32))
+        got = _native.Context.align_batch_sharded(ctxs, bounds, buf, t_off, n, o_off, m, params, out=out)
+        assert got[0] is out[0]
+        assert np.array_equal(one[2], got[2]) and np.array_equal(one[3], got[3])
+        for k in range(P):
+            assert np.array_equal(one[0][one[1][k]:one[1][k] + one[2][k]], got[0][got[1][k]:got[1][k] + got[2][k]])
+        assert (out[0][total:] == 9).all()
+    bad_n = n.copy(); bad_n[200] = -3
+    with pytest.raises(ValueError) as e:               # TANW_E_INVALID, as from tanw_align_batch
+        _native.Context.align_batch_sharded(ctxs, [0, 100, 250, P], buf, t_off, bad_n, o_off, m, params)
+    assert 'shard 1' in str(e.value)
+    with pytest.raises(ValueError):
+        _native.Context.align_batch_sharded([ctxs[0], ctxs[0]], [0, 10, P], buf, t_off, n, o_off, m, params)
+    with pytest.raises(ValueError):
+        _native.Context.align_batch_sharded(ctxs, [0, 10, 5, P], buf, t_off, n, o_off, m, params)
+    packed = _native.Context(0)
+    packed.set_packed_ops(True)
+    with pytest.raises(_native.NativeError):
+        _native.Context.align_batch_sharded([ctxs[0], packed], [0, 10, P], buf, t_off, n, o_off, m, params)
+    # the contexts are still usable
+    again = _native.Context.align_batch_sharded(ctxs, [0, 100, 250, P], buf, t_off, n, o_off, m, params)
+    assert np.array_equal(one[2], again[2])
+
+
 def _sharded_worker(rank, world, port, q):
     import os
     import torch.distributed as dist

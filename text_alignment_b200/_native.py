@@ -58,6 +58,9 @@ SIGNATURES = {
     'tanw_align_batch_multi': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                               ctypes.POINTER(Scoring), ctypes.c_int32, _i32p,
                                               _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
+    'tanw_align_batch_sharded': (ctypes.c_int, [ctypes.POINTER(_VOIDP), ctypes.c_int32, _i64p,
+                                                _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
+                                                ctypes.POINTER(Scoring), _u8p, _i64p, ctypes.c_int64, _i32p, _i32p]),
     'tanw_batch_prepare_multi': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
                                                 ctypes.POINTER(Scoring), ctypes.c_int32, _i32p]),
     'tanw_batch_prepare': (ctypes.c_int, [_VOIDP, _u8p, ctypes.c_int64, _i64p, _i32p, _i64p, _i32p, ctypes.c_int64,
@@ -397,6 +400,46 @@ class Context(object):
                                             _ptr(scores, _i32p) if want_scores else None)
             self._check(rc)
         return ops, ops_off, ops_len[:P], (scores[:P] if want_scores else None)
+
+    @staticmethod
+    def align_batch_sharded(contexts, bounds, symbols, t_off, n, o_off, m, scoring_params, subst=None,
+                            want_scores=True, out=None, layout=None):
+        """One batch over several contexts (devices): shard d = pairs bounds[d]..bounds[d+1]-1 on
+        contexts[d], one native host thread per shard (tanw_align_batch_sharded), results written
+        straight into the batch's arrays.  Returns (ops, ops_off, ops_len, scores)."""
+        first = contexts[0]
+        symbols, t_off, n, o_off, m = first._canon(symbols, t_off, n, o_off, m)
+        bounds = np.ascontiguousarray(bounds, dtype=np.int64)
+        if bounds.size != len(contexts) + 1:
+            raise ValueError('bounds must have one more entry than there are contexts')
+        P = int(n.size)
+        ops_off, total = layout if layout is not None else Context.canonical_ops_layout(n, m)
+        if out is not None:
+            ops, ops_len, scores = out
+            if (ops.size < total and total > 0) or ops_len.size < P or (want_scores and scores.size < 3 * P):
+                raise ValueError('preallocated output buffers are too small')
+        else:
+            ops = np.empty(max(total, 1), dtype=np.uint8)
+            ops_len = np.zeros(max(P, 1), dtype=np.int32)
+            scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
+        sc, keep = first.make_scoring(*scoring_params, subst=subst)
+        handles = (_VOIDP * len(contexts))(*[c._h for c in contexts])
+        locks = sorted(set(contexts), key=id)
+        for c in locks:
+            c.lock.acquire()
+        try:
+            for c in contexts:
+                c._symbol_width(symbols)
+            rc = first._lib.tanw_align_batch_sharded(handles, len(contexts), _ptr(bounds, _i64p),
+                                                     symbols.ctypes.data_as(_u8p), symbols.size, _ptr(t_off, _i64p),
+                                                     _ptr(n, _i32p), _ptr(o_off, _i64p), _ptr(m, _i32p), P,
+                                                     ctypes.byref(sc), _ptr(ops, _u8p), _ptr(ops_off, _i64p), ops.size,
+                                                     _ptr(ops_len, _i32p), _ptr(scores, _i32p) if want_scores else None)
+            first._check(rc)
+        finally:
+            for c in reversed(locks):
+                c.lock.release()
+        return ops, ops_off, ops_len[:P], (scores.reshape(-1, 3)[:P] if want_scores else None)
 
     def align_batch_multi(self, symbols, t_off, n, o_off, m, scorings, scoring_idx, want_scores=True):
         """Every pair under its own scoring system (the reference's parameter sweep as one launch):

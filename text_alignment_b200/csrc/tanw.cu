@@ -35,6 +35,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace tanw;
@@ -1375,6 +1376,76 @@ int tanw_align_batch_multi(tanw_ctx *ctx, const uint8_t *symbols, int64_t symbol
     PrepareInput in = { symbols, symbols_len, t_off, o_off, n, m, n_pairs, scorings, n_scorings,
                         scoring_idx ? scoring_idx : &none, true };
     return align_impl(ctx, in, ops, ops_off, ops_capacity, ops_len, scores);
+}
+
+// One batch over several devices: shard d = pairs [bounds[d], bounds[d+1]) on ctxs[d], one host
+// thread per shard.  Pairs are independent (alignToOCR.py:273 is one call per page), so there is
+// no exchange step: every shard writes its op strings, lengths and scores straight into its slice
+// of the caller's arrays.
+int tanw_align_batch_sharded(tanw_ctx *const *ctxs, int32_t n_ctx, const int64_t *bounds,
+                             const uint8_t *symbols, int64_t symbols_len,
+                             const int64_t *t_off, const int32_t *n, const int64_t *o_off, const int32_t *m,
+                             int64_t n_pairs, const tanw_scoring *scoring, uint8_t *ops, const int64_t *ops_off,
+                             int64_t ops_capacity, int32_t *ops_len, int32_t *scores)
+{
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return fail(nullptr, TANW_E_INVALID, "no context");
+    tanw_ctx *first = ctxs[0];
+    if (!bounds) return fail(first, TANW_E_INVALID, "bounds is NULL");
+    if (n_pairs < 0) return fail(first, TANW_E_INVALID, "n_pairs must be >= 0");
+    if (n_pairs > 0 && (!t_off || !n || !o_off || !m || !ops_off || !ops_len))
+        return fail(first, TANW_E_INVALID, "NULL pair table");
+    if (bounds[0] != 0 || bounds[n_ctx] != n_pairs) return fail(first, TANW_E_INVALID, "bounds must run from 0 to n_pairs");
+    for (int d = 0; d < n_ctx; ++d) {
+        if (!ctxs[d]) return fail(first, TANW_E_INVALID, "context %d is NULL", d);
+        if (bounds[d + 1] < bounds[d]) return fail(first, TANW_E_INVALID, "bounds must not decrease");
+        if (ctxs[d]->packed_ops) return fail(first, TANW_E_STATE, "packed op strings are per context: not with a sharded batch");
+        if (ctxs[d]->sym_bytes != first->sym_bytes) return fail(first, TANW_E_STATE, "contexts differ in symbol width");
+        for (int e = 0; e < d; ++e)
+            if (ctxs[e] == ctxs[d]) return fail(first, TANW_E_INVALID, "context %d is listed twice", d);
+    }
+    std::vector<int> rcs((size_t)n_ctx, TANW_OK);
+    auto shard = [&](int d) {
+        const int64_t lo = bounds[d], hi = bounds[d + 1], P = hi - lo;
+        if (P <= 0) return;
+        try {
+            // the smallest contiguous slice of the symbol buffer that holds the shard
+            int64_t s_lo = INT64_MAX, s_hi = 0;
+            for (int64_t p = lo; p < hi; ++p) {
+                s_lo = std::min(s_lo, std::min(t_off[p], o_off[p]));
+                s_hi = std::max(s_hi, std::max(t_off[p] + std::max(n[p], 0), o_off[p] + std::max(m[p], 0)));
+            }
+            if (s_lo < 0 || s_hi > symbols_len || s_lo > s_hi) { s_lo = 0; s_hi = symbols_len; }   // the shard's own check names the pair
+            std::vector<int64_t> t((size_t)P), o((size_t)P), oo((size_t)P);
+            const int64_t ops_lo = ops_off[lo];
+            for (int64_t p = 0; p < P; ++p) {
+                t[(size_t)p] = t_off[lo + p] - s_lo;
+                o[(size_t)p] = o_off[lo + p] - s_lo;
+                oo[(size_t)p] = ops_off[lo + p] - ops_lo;
+            }
+            const int64_t ops_hi = hi < n_pairs ? ops_off[hi] : ops_capacity;
+            rcs[(size_t)d] = tanw_align_batch(ctxs[d], symbols + s_lo * ctxs[d]->sym_bytes, s_hi - s_lo, t.data(), n + lo,
+                                              o.data(), m + lo, P, scoring, ops + ops_lo, oo.data(), ops_hi - ops_lo,
+                                              ops_len + lo, scores ? scores + 3 * lo : nullptr);
+        } catch (const std::bad_alloc &) {
+            rcs[(size_t)d] = fail(ctxs[d], TANW_E_NOMEM, "out of host memory for the shard tables");
+        }
+    };
+    std::vector<std::thread> threads;
+    try {
+        for (int d = 1; d < n_ctx; ++d) threads.emplace_back(shard, d);
+    } catch (...) {
+        for (auto &th : threads) th.join();
+        return fail(first, TANW_E_INTERNAL, "could not start a host thread per device");
+    }
+    shard(0);
+    for (auto &th : threads) th.join();
+    for (int d = 0; d < n_ctx; ++d)
+        if (rcs[(size_t)d] != TANW_OK) {
+            if (d > 0) return fail(first, rcs[(size_t)d], "shard %d (pairs %lld..%lld): %s", d, (long long)bounds[d],
+                                   (long long)bounds[d + 1], ctxs[d]->err.c_str());
+            return rcs[0];
+        }
+    return TANW_OK;
 }
 
 int tanw_last_timing(tanw_ctx *ctx, tanw_timing *out)

@@ -497,43 +497,12 @@ def align_packed(symbols, t_off, n, o_off, m, params, subst=None, devices=None, 
         ctx = get_context(devices[0])
         return ctx.align_batch(symbols, t_off, n, o_off, m, ctx.make_scoring(*params, subst=subst),
                                want_scores=want_scores, out=out)
-    P = int(n.size)
     bounds = split_by_cells(n, m, len(devices))
-    ops_off, total = _native.Context.canonical_ops_layout(n, m)
-    if out is not None:
-        ops, ops_len, scores = out
-        if ops.size < total or ops_len.size < P or (want_scores and scores.size < 3 * P):
-            raise ValueError('preallocated output buffers are too small')
-    else:
-        ops = np.empty(max(total, 1), dtype=np.uint8)
-        ops_len = np.zeros(max(P, 1), dtype=np.int32)
-        scores = np.zeros((max(P, 1), 3), dtype=np.int32) if want_scores else None
-    errs = [None] * len(devices)
-
-    def work(d):
-        lo, hi = int(bounds[d]), int(bounds[d + 1])
-        if hi <= lo:
-            return
-        try:
-            ctx = get_context(devices[d], replica=devices[:d].count(devices[d]))
-            sub_sym, sub_t, sub_o = _rebase(symbols, t_off[lo:hi], n[lo:hi], o_off[lo:hi], m[lo:hi])
-            base = int(ops_off[lo])
-            end = int(ops_off[hi]) if hi < P else total
-            shard_out = (ops[base:max(end, base + 1)], ops_len[lo:hi],
-                         scores.reshape(-1, 3)[lo:hi] if want_scores else None)
-            ctx.align_batch(sub_sym, sub_t, n[lo:hi], sub_o, m[lo:hi], ctx.make_scoring(*params, subst=subst),
-                            want_scores=want_scores, out=shard_out, layout=(ops_off[lo:hi] - base, end - base))
-        except BaseException as e:       # re-raised on the caller's thread
-            errs[d] = e
-    threads = [threading.Thread(target=work, args=(d,)) for d in range(len(devices))]
-    for th in threads:
-        th.start()
-    for th in threads:
-        th.join()
-    for e in errs:
-        if e is not None:
-            raise e
-    return ops, ops_off, ops_len[:P], (scores.reshape(-1, 3)[:P] if want_scores else None)
+    contexts = [get_context(dev, replica=devices[:d].count(dev)) for d, dev in enumerate(devices)]
+    # one native host thread per shard (tanw_align_batch_sharded): Python threads would take turns
+    # at the interpreter lock for their share of the call's host work before any device starts
+    return _native.Context.align_batch_sharded(contexts, bounds, symbols, t_off, n, o_off, m, params, subst=subst,
+                                               want_scores=want_scores, out=out)
 
 
 def _rebase(symbols, t_off, n, o_off, m):
