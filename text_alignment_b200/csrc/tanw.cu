@@ -624,7 +624,10 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
             // Lines (with the odd page among them): chunks pay when the copies are long next to what
             // a chunk boundary costs (a few small launches), and a chunk should be whole rounds of
             // the line kernel's resident warps (eight pairs each).
-            const double want = std::sqrt(copy_ms / 0.012);     // (successive chunks' line kernels overlap: a boundary is cheap)
+            double want = std::sqrt(copy_ms / 0.012);           // (successive chunks' line kernels overlap: a boundary is cheap)
+#ifdef TANW_TUNING
+            if (const char *e = getenv("TANW_LINE_CHUNKS")) want = atof(e);                  // tuning builds only
+#endif
             while (S * 2 <= std::min<int>(n_slices, kMaxChunks) && S * 2 <= want) S *= 2;
             if (S > 1) {
                 const double per_round = (double)ctx->sm_count * ctx->occ_line16 * kWarpsPerBlock * 8 / (double)slice_pairs;
@@ -871,6 +874,9 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
     TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned) * 4 * kMaxChunks, ctx->s_k));
     TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_misc.p, 0, sizeof(int), ctx->s_k));
     bool cp_forked[kMaxChunks] = {}, cp_lines[kMaxChunks] = {};
+    // (Building the tables of all chunks of a line batch up front, before its first line kernel,
+    // is slower -- config 3 end to end 1.29 -> 1.58 ms: a chunk's table kernels find free SM slots
+    // beside the previous chunk's line kernel, so built lazily they cost nothing.)
     for (int c = 0; c < ctx->n_chunks; ++c) {
         if (int rc = build_chunk_tables(ctx, c)) return rc;
         const ChunkPlan &cp = ctx->chunk[c];
