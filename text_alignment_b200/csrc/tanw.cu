@@ -111,6 +111,9 @@ struct tanw_ctx {
     cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_k3 = nullptr, s_l0 = nullptr, s_l1 = nullptr, s_out = nullptr;
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr,
                 ev_d2h0 = nullptr, ev_d2h1 = nullptr, ev_tab = nullptr, ev_survey = nullptr, ev_idle = nullptr;
+#ifdef TANW_TUNING
+    cudaEvent_t tl_ls[kMaxChunks] = {}, tl_le[kMaxChunks] = {}, tl_d[kMaxChunks] = {};   // timeline of a pipelined call (TANW_TIMELINE)
+#endif
     cudaEvent_t ev_piece[kPieces] = {}, ev_chunk[kMaxChunks] = {}, ev_fork[kMaxChunks] = {}, ev_pages[kMaxChunks] = {},
                 ev_lines[kMaxChunks] = {};
     std::string err;
@@ -494,14 +497,6 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_tab, ctx->s_in));
     const int64_t sym_bytes_total = in.symbols_len * sb;
     const int64_t piece_bytes = std::max<int64_t>((sym_bytes_total + kPieces - 1) / kPieces / 256 * 256 + 256, 1 << 16);
-    for (int i = 0; i < kPieces; ++i) {
-        const int64_t lo = std::min(sym_bytes_total, piece_bytes * i), hi = std::min(sym_bytes_total, piece_bytes * (i + 1));
-        if (hi > lo)
-            TANW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_sym.p + lo, in.symbols + lo, (size_t)(hi - lo),
-                                           cudaMemcpyHostToDevice, ctx->s_in));
-        TANW_CUDA(ctx, cudaEventRecord(ctx->ev_piece[i], ctx->s_in));
-    }
-    h2d += sym_bytes_total;
 
     // ---- the survey: sizes, routes, validation, on the device; the host waits for 1 KB ----------
     int64_t limit = ctx->arena_limit;
@@ -536,7 +531,16 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     }
     TANW_CUDA(ctx, cudaMemcpyAsync(&sv, ctx->d_survey.p, survey_head, cudaMemcpyDeviceToHost, ctx->s_k));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_survey, ctx->s_k));
-    // host work that does not need the survey runs while it is on its way
+    // host work that does not need the survey runs while it is on its way: first of all the symbol
+    // upload, in pieces with an event each, so that a chunk's kernels wait only for their own symbols
+    for (int i = 0; i < kPieces; ++i) {
+        const int64_t lo = std::min(sym_bytes_total, piece_bytes * i), hi = std::min(sym_bytes_total, piece_bytes * (i + 1));
+        if (hi > lo)
+            TANW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_sym.p + lo, in.symbols + lo, (size_t)(hi - lo),
+                                           cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaEventRecord(ctx->ev_piece[i], ctx->s_in));
+    }
+    h2d += sym_bytes_total;
     int64_t pmax = 1;
     int var = 2;
     for (int32_t i = 0; i < (multi ? in.n_sc : 1); ++i) {
@@ -888,6 +892,9 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
         if (forked || lines_away) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_fork[c], ctx->s_k));
         if (lines_away) TANW_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->ev_fork[c], 0));
         if (pipelined && (has_lines || !forked)) TANW_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->ev_piece[cp.piece], 0));
+#ifdef TANW_TUNING
+        TANW_CUDA(ctx, cudaEventRecord(ctx->tl_ls[c], ls));
+#endif
         if (cp.n_octets > 0) {
             LineArgs la = ctx->largs;
             la.ptr_arena += (size_t)lpar * (size_t)ctx->line_arena_bytes;
@@ -915,6 +922,9 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             if (int rc = pack_chunk(ctx, cp, (1u << kRouteLine) | (1u << kRouteLine16), ls)) return rc;
             ++launches;
         }
+#ifdef TANW_TUNING
+        TANW_CUDA(ctx, cudaEventRecord(ctx->tl_le[c], ls));
+#endif
         if (lines_away) TANW_CUDA(ctx, cudaEventRecord(ctx->ev_lines[c], ls));
         cp_lines[c] = lines_away;
         if (cp.n_page > 0) {
@@ -1026,10 +1036,30 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
                 d2h += (int64_t)sizeof(int) * 3 * cp.count;
             }
         }
+#ifdef TANW_TUNING
+        TANW_CUDA(ctx, cudaEventRecord(ctx->tl_d[c], ctx->s_out));
+#endif
     }
     TANW_CUDA(ctx, cudaMemcpyAsync(ctx->h_misc, ctx->d_misc.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_d2h1, ctx->s_out));
     TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+#ifdef TANW_TUNING
+    if (getenv("TANW_TIMELINE")) {                                  // tuning builds only: ms since the first upload
+        float t = 0.f;
+        for (int i = 0; i < kPieces; ++i)
+            if (cudaEventElapsedTime(&t, ctx->ev_h2d0, ctx->ev_piece[i]) == cudaSuccess) fprintf(stderr, "piece %d in %.3f\n", i, t);
+        for (int c = 0; c < ctx->n_chunks; ++c) {
+            float a = 0.f, b = 0.f, d = 0.f;
+            cudaEventElapsedTime(&a, ctx->ev_h2d0, ctx->tl_ls[c]);
+            cudaEventElapsedTime(&b, ctx->ev_h2d0, ctx->tl_le[c]);
+            cudaEventElapsedTime(&d, ctx->ev_h2d0, ctx->tl_d[c]);
+            fprintf(stderr, "chunk %d (piece %d, %lld pairs): lines %.3f .. %.3f, copied out %.3f\n", c, ctx->chunk[c].piece,
+                    (long long)ctx->chunk[c].count, a, b, d);
+        }
+        if (cudaEventElapsedTime(&t, ctx->ev_h2d0, ctx->ev_d2h1) == cudaSuccess) fprintf(stderr, "done %.3f\n", t);
+        cudaGetLastError();
+    }
+#endif
     if (ctx->h_misc[0] != 0)
         return fail(ctx, TANW_E_INTERNAL, "device assertion %d failed (TANW_CHECKED build)", ctx->h_misc[0]);
     if (!canonical) {
@@ -1141,12 +1171,21 @@ int tanw_create(int device, tanw_ctx **out)
     for (auto ev : plain)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     for (int i = 0; i < kPieces; ++i)
+#ifdef TANW_TUNING
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_piece[i]);
+#else
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_piece[i], cudaEventDisableTiming);
+#endif
     for (int i = 0; i < kMaxChunks; ++i) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pages[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lines[i], cudaEventDisableTiming);
+#ifdef TANW_TUNING
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->tl_ls[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->tl_le[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->tl_d[i]);
+#endif
     }
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_survey, sizeof(Survey));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_misc, 256);
@@ -1198,6 +1237,13 @@ int tanw_destroy(tanw_ctx *ctx)
         if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_lines)
         if (ev) cudaEventDestroy(ev);
+#ifdef TANW_TUNING
+    for (int i = 0; i < kMaxChunks; ++i) {
+        if (ctx->tl_ls[i]) cudaEventDestroy(ctx->tl_ls[i]);
+        if (ctx->tl_le[i]) cudaEventDestroy(ctx->tl_le[i]);
+        if (ctx->tl_d[i]) cudaEventDestroy(ctx->tl_d[i]);
+    }
+#endif
     if (ctx->h_survey) cudaFreeHost(ctx->h_survey);
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
     if (ctx->h_subst) cudaFreeHost(ctx->h_subst);
