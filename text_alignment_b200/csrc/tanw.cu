@@ -634,7 +634,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
 #endif
             while (S * 2 <= std::min<int>(n_slices, kMaxChunks) && S * 2 <= want) S *= 2;
             if (S > 1) {
-                const double per_round = (double)ctx->sm_count * ctx->occ_line16 * kWarpsPerBlock * 8 / (double)slice_pairs;
+                const double per_round = (double)ctx->sm_count * ctx->occ_line16 * kL16Warps * 8 / (double)slice_pairs;
                 const double rounds = std::max(1.0, std::floor((double)n_slices / S / per_round + 0.5));
                 per = (int)std::max(1.0, std::floor(rounds * per_round));
                 if ((n_slices + per - 1) / per > kMaxChunks) per = (n_slices + kMaxChunks - 1) / kMaxChunks;
@@ -738,13 +738,13 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     if (const char *e = getenv("TANW_LINE16_BLOCKS")) occ16 = std::max(1, std::min(occ16, atoi(e)));   // tuning builds only
 #endif
     int line16_grid = ctx->sm_count * occ16;
-    if (((int64_t)max_octets + kWarpsPerBlock - 1) / kWarpsPerBlock < line16_grid)
-        line16_grid = (int)std::max<int64_t>(((int64_t)max_octets + kWarpsPerBlock - 1) / kWarpsPerBlock, 1);
+    if (((int64_t)max_octets + kL16Warps - 1) / kL16Warps < line16_grid)
+        line16_grid = (int)std::max<int64_t>(((int64_t)max_octets + kL16Warps - 1) / kL16Warps, 1);
     const int64_t line16_slot = (max_line16_slot + 255) / 256 * 256;
     ctx->line16_grid = line16_grid;
     ctx->line16_slot = line16_slot;
     ctx->line16_max_n = n_line16_total > 0 ? std::max(max_nm16, 1) : 0;     // the tallest pair routed to the 16-bit kernel
-    if (max_octets) line_arena = std::max(line_arena, (int64_t)line16_grid * kWarpsPerBlock * 8 * line16_slot);
+    if (max_octets) line_arena = std::max(line_arena, (int64_t)line16_grid * kL16Warps * 8 * line16_slot);
     line_arena = (line_arena + 255) / 256 * 256;
     if (alt_lines && arenas * slots * slot_bytes + 2 * line_arena > limit) alt_lines = false;
     const int bnd_rows = max_n + 4;      // bnd[1..n] plus the prefetch overrun
@@ -903,7 +903,7 @@ int run_impl(tanw_ctx *ctx, bool pipelined)
             la.counter = (unsigned *)ctx->d_counter.p + 4 * c + 2;
             la.slot_bytes = ctx->line16_slot;
             la.n_quads = cp.n_octets;
-            const int grid = (int)std::min<int64_t>(ctx->line16_grid, ((int64_t)cp.n_octets + kWarpsPerBlock - 1) / kWarpsPerBlock);
+            const int grid = (int)std::min<int64_t>(ctx->line16_grid, ((int64_t)cp.n_octets + kL16Warps - 1) / kL16Warps);
             TANW_CUDA(ctx, launch_lines16(la, ctx->kp, ctx->var, std::max(grid, 1), ls));
             ++launches;
         }

@@ -31,15 +31,15 @@ cudaError_t launch_lines(const LineArgs &a, const KParams &kp, int var, bool sub
 
 cudaError_t launch_lines16(const LineArgs &a, const KParams &kp, int var, int grid, cudaStream_t stream)
 {
-    if (var == 2) align_lines16_kernel<2><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, kp);
-    else          align_lines16_kernel<1><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, kp);
+    if (var == 2) align_lines16_kernel<2><<<grid, kL16Warps * 32, 0, stream>>>(a, kp);
+    else          align_lines16_kernel<1><<<grid, kL16Warps * 32, 0, stream>>>(a, kp);
     return cudaGetLastError();
 }
 
 int lines16_blocks_per_sm()
 {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_lines16_kernel<1>, kWarpsPerBlock * 32, 0) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_lines16_kernel<1>, kL16Warps * 32, 0) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }

@@ -34,12 +34,19 @@
 #ifndef TANW_L16_LDPOL
 #define TANW_L16_LDPOL 1
 #endif
+#ifndef TANW_L16_WARPS
+#define TANW_L16_WARPS 4
+#endif
 #ifndef TANW_L16_PREFETCH
 #define TANW_L16_PREFETCH 1
 #endif
 
 namespace tanw {
 
+// warps per block of the 16-bit line kernel.  Blocks of 1 / 2 warps (a slot frees as soon as ONE
+// warp is done, which should suit the one-octet-per-warp chunks of a pipelined call) measured
+// slower: 0.812 / 0.786 ms per config-3 launch against 0.783, 690 / 710 GCUPS end to end against 740.
+constexpr int kL16Warps = TANW_L16_WARPS;
 constexpr int kBias16 = 8192;                 // value + kBias16 in [0, 16383]
 constexpr int kRange16 = 8000;                // |value| bound the host guarantees for every half
 constexpr unsigned kClean16 = 0xFFFCFFFCu;
@@ -512,14 +519,14 @@ __device__ __forceinline__ void line_octet(const LineArgs &a, const KParams &kp3
 }
 
 template <int VAR>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, TANW_MINB)
+__global__ void __launch_bounds__(kL16Warps * 32, TANW_MINB * kWarpsPerBlock / kL16Warps)
 align_lines16_kernel(const LineArgs a, const __grid_constant__ KParams kp32)
 {
-    __shared__ unsigned tiles[kWarpsPerBlock][4 * 2 * kL16TileWords];
+    __shared__ unsigned tiles[kL16Warps][4 * 2 * kL16TileWords];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane >> 3;
-    const long long slot = (((long long)blockIdx.x * kWarpsPerBlock + warp) * 4 + g) * 2;
+    const long long slot = (((long long)blockIdx.x * kL16Warps + warp) * 4 + g) * 2;
     uint8_t *const ptrA = a.ptr_arena + (size_t)slot * (size_t)a.slot_bytes;
     uint8_t *const ptrB = ptrA + (size_t)a.slot_bytes;
     unsigned *const tile = tiles[warp] + g * (2 * kL16TileWords);
