@@ -535,6 +535,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     // upload, in pieces with an event each, so that a chunk's kernels wait only for their own symbols
     for (int i = 0; i < kPieces; ++i) {
         const int64_t lo = std::min(sym_bytes_total, piece_bytes * i), hi = std::min(sym_bytes_total, piece_bytes * (i + 1));
+        if (hi <= lo && i > 0) break;                   // a chunk waits for the piece its last symbol is in: never an empty one
         if (hi > lo)
             TANW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_sym.p + lo, in.symbols + lo, (size_t)(hi - lo),
                                            cudaMemcpyHostToDevice, ctx->s_in));

@@ -322,7 +322,14 @@ __device__ __forceinline__ Chain no_chain()
     c.r0 = 0; c.ck_in = nullptr; c.ck_out = nullptr; c.m = 0; c.store = true; c.check = nullptr; c.stage = nullptr;
     return c;
 }
-constexpr int kChainBlock = 8;         // boundary rows fetched per coalesced load (lanes 0..7)
+// Hand-over records fetched per asynchronous copy (one per lane 0 .. kChainBlock-1).  A larger block
+// adds rows of lag per stripe but halves the take / issue work per row; measured on config 5 /
+// a single page: 2 -> 20.6 ms / 0.320 ms, 4 -> 17.2 / 0.272, 8 -> 16.15 / 0.260, 16 -> 15.98 / 0.253,
+// 32 -> 16.0 / 0.253.
+#ifndef TANW_CHAIN_BLOCK
+#define TANW_CHAIN_BLOCK 16
+#endif
+constexpr int kChainBlock = TANW_CHAIN_BLOCK;
 
 __device__ __forceinline__ int4 ld_volatile_v4(const int4 *p)
 {
@@ -336,9 +343,9 @@ __device__ __forceinline__ void st_volatile_v4(int4 *p, int4 v)
     asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// Rows base .. base+7 of the left stripe's edge, one per lane 0..7.  chain_issue only starts the
-// copy; chain_take, called a block (8 steps) later, checks the stamps and spins only if the
-// producer has not got there yet -- so the L2 round trip overlaps the 8 steps in between
+// Rows base .. base+kChainBlock-1 of the left stripe's edge, one per lane.  chain_issue only starts the
+// copy; chain_take, called a block (kChainBlock steps) later, checks the stamps and spins only if the
+// producer has not got there yet -- so the L2 round trip overlaps the steps in between
 // (ncu: with a blocking fetch a stripe spent a third of its time in this load).  The copy is an
 // asynchronous one into shared memory (LDGSTS) rather than a load into registers: ptxas puts every
 // global load of the loop on one scoreboard, so the per-step transcript byte -- an L1 hit -- waited
@@ -390,13 +397,13 @@ __device__ __forceinline__ void pass_step(Strip<C> &s, PassState &ps, const KPar
     if (!GUARDED || t + 1 <= n) {
         if (CHAINED) {
             // A chained stripe has an SM sub-partition almost to itself, so a load issued one
-            // step ahead does not hide L2 latency.  The boundary arrives in blocks of 8 rows
+            // step ahead does not hide L2 latency.  The boundary arrives in blocks of kChainBlock rows
             // (one coalesced load per block, fetched a block ahead) and reaches lane 0 by shuffle.
             // Stripe 0 reads column 0 of the matrices the same way (records written by
             // long_col0_kernel), so that the loop has no per-stripe special case.
             const int r = t + 1;                          // boundary row needed by the next step
             const int j = (r - 1) & (kChainBlock - 1);
-            if (j == 0) {                         // rows r .. r+7 were requested 8 steps ago
+            if (j == 0) {                         // this block was requested a block ago
                 ps.blk_cur = chain_take(ch, r, n, lane);
                 if (r + kChainBlock <= n) chain_issue(ch, r + kChainBlock, n, lane);
             }
