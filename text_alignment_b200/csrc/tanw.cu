@@ -110,7 +110,7 @@ struct tanw_ctx {
     int sm_count = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_k3 = nullptr, s_l0 = nullptr, s_l1 = nullptr, s_out = nullptr;
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr,
-                ev_d2h0 = nullptr, ev_d2h1 = nullptr, ev_tab = nullptr, ev_survey = nullptr, ev_idle = nullptr;
+                ev_d2h0 = nullptr, ev_d2h1 = nullptr, ev_tab = nullptr, ev_survey = nullptr, ev_idle = nullptr, ev_small = nullptr;
 #ifdef TANW_TUNING
     cudaEvent_t tl_ls[kMaxChunks] = {}, tl_le[kMaxChunks] = {}, tl_d[kMaxChunks] = {};   // timeline of a pipelined call (TANW_TIMELINE)
 #endif
@@ -126,6 +126,7 @@ struct tanw_ctx {
            d_misc, d_pack;
     Survey *h_survey = nullptr;           // pinned: the device's report on the batch
     int *h_misc = nullptr;                // pinned: [0] device assertion word, [1] largest symbol code
+    uint8_t *h_small = nullptr;           // pinned: pair descriptors + routes of a handful of pairs built by the host
     int *h_subst = nullptr;               // pinned copy of the substitution table in kernel encoding
     size_t h_subst_cap = 0;
     KParams *h_kparams = nullptr;         // pinned: per-pair scoring systems of a multi batch
@@ -441,6 +442,57 @@ struct PrepareInput {
     bool pipelined;                       // cut into chunks when that pays (tanw_align_batch)
 };
 
+// The survey of a handful of pairs, by the host from the arrays it was given: the per-pair rules of
+// survey_kernel (tanw_tables.cuh) word for word.  A single page per call is the reference's own
+// pattern (alignToOCR.py:273); waiting for the device's report and then for its list of
+// chained-stripe pairs costs two round trips of ~30 us each, a sixth of such a call.
+constexpr int64_t kHostSurveyPairs = 64;
+void host_survey(const TableArgs &a, const PrepareInput &in, Survey &sv)
+{
+    memset(&sv, 0, offsetof(Survey, long_list));
+    ChunkSurvey &cs = sv.chunk[0];
+    int64_t bad = -1;
+    for (int64_t p = 0; p < in.n_pairs; ++p) {
+        const long long np = in.n[p], mp = in.m[p], to = in.t_off[p], oo = in.o_off[p];
+        if (np < 0 || mp < 0 || to < 0 || oo < 0 || to + np > a.symbols_len || oo + mp > a.symbols_len) {
+            if (bad < 0) bad = p;
+            continue;
+        }
+        cs.cap += np + mp;
+        cs.cells += np * mp;
+        cs.sym_end = std::max<long long>(cs.sym_end, std::max(to + np, oo + mp));
+        sv.max_nm = std::max(sv.max_nm, (int)std::min<long long>(np + mp, 0x7fffffffll));
+        const int cls = (np > 0 && mp > 0) ? line_c((int)mp) / 4 - 1 : 0;
+        switch (route_of(a, np, mp)) {
+        case kRouteLong:
+            ++cs.n_long;
+            if (sv.n_long < kMaxLongList) sv.long_list[sv.n_long] = (int)p;
+            ++sv.n_long;
+            break;
+        case kRouteLine:
+            ++cs.n_line;
+            cs.max_line_slot = std::max(cs.max_line_slot, line_ptr_bytes((int)np, (int)mp));
+            ++cs.line_class[cls];
+            break;
+        case kRouteLine16:
+            ++cs.n_line16;
+            cs.max_nm_line16 = std::max(cs.max_nm_line16, (int)(np + mp));
+            cs.max_n_line16 = std::max(cs.max_n_line16, (int)np);
+            cs.max_line16_slot = std::max(cs.max_line16_slot, line_ptr_bytes((int)np, (int)mp));
+            ++cs.line16_class[cls];
+            break;
+        default:
+            ++cs.n_page;
+            cs.page_cells += np * mp;
+            cs.max_slot = std::max(cs.max_slot, ptr_bytes((int)np, (int)mp));
+            cs.max_page_cells = std::max(cs.max_page_cells, np * mp);
+            cs.max_n_page = std::max(cs.max_n_page, (int)np);
+            break;
+        }
+    }
+    sv.bad = bad >= 0 ? 0xFFFFFFFFFFFFFFFFull - (unsigned long long)bad : 0;
+}
+
 int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
 {
     if (!ctx) return fail(nullptr, TANW_E_INVALID, "ctx is NULL");
@@ -523,14 +575,23 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ta.tile_sums = (long long *)ctx->d_tilesums.p;
     Survey &sv = *ctx->h_survey;
     const size_t survey_head = offsetof(Survey, long_list);
+    const bool host_sv = P <= kHostSurveyPairs;
+    if (host_sv) host_survey(ta, in, sv);
+    // ... and when every one of them takes the chained-stripe path (a single page per call), the host
+    // writes their descriptors too: no survey and no table kernels at all
+    const bool host_tables = host_sv && P > 0 && sv.bad == 0 && sv.n_long == P && !ctx->packed_ops;
     TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_tab, 0));
-    TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_survey.p, 0, survey_head, ctx->s_k));
-    if (n_tiles > 0) {
-        survey_kernel<<<(unsigned)n_tiles, kTileThreads, 0, ctx->s_k>>>(ta);
-        TANW_CUDA(ctx, cudaGetLastError());
+    if (!host_tables) {
+        TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_survey.p, 0, survey_head, ctx->s_k));
+        if (n_tiles > 0) {                                // (also beside a host survey: the table kernels use its tile sums)
+            survey_kernel<<<(unsigned)n_tiles, kTileThreads, 0, ctx->s_k>>>(ta);
+            TANW_CUDA(ctx, cudaGetLastError());
+        }
     }
-    TANW_CUDA(ctx, cudaMemcpyAsync(&sv, ctx->d_survey.p, survey_head, cudaMemcpyDeviceToHost, ctx->s_k));
-    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_survey, ctx->s_k));
+    if (!host_sv) {
+        TANW_CUDA(ctx, cudaMemcpyAsync(&sv, ctx->d_survey.p, survey_head, cudaMemcpyDeviceToHost, ctx->s_k));
+        TANW_CUDA(ctx, cudaEventRecord(ctx->ev_survey, ctx->s_k));
+    }
     // host work that does not need the survey runs while it is on its way: first of all the symbol
     // upload, in pieces with an event each, so that a chunk's kernels wait only for their own symbols
     for (int i = 0; i < kPieces; ++i) {
@@ -557,7 +618,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
             return fail(ctx, TANW_E_NOMEM, "out of host memory");
         }
     }
-    TANW_CUDA(ctx, cudaEventSynchronize(ctx->ev_survey));
+    if (!host_sv) TANW_CUDA(ctx, cudaEventSynchronize(ctx->ev_survey));
 
     if (sv.bad != 0) {
         const int64_t p = (int64_t)(0xFFFFFFFFFFFFFFFFull - sv.bad);
@@ -578,9 +639,11 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ctx->longs.clear();
     int64_t max_long = 0, max_long_bnd = 0, max_ck = 0;
     if (sv.n_long > 0) {
-        TANW_CUDA(ctx, cudaMemcpyAsync(sv.long_list, (const uint8_t *)ctx->d_survey.p + survey_head,
-                                       sizeof(int) * (size_t)sv.n_long, cudaMemcpyDeviceToHost, ctx->s_k));
-        TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
+        if (!host_sv) {
+            TANW_CUDA(ctx, cudaMemcpyAsync(sv.long_list, (const uint8_t *)ctx->d_survey.p + survey_head,
+                                           sizeof(int) * (size_t)sv.n_long, cudaMemcpyDeviceToHost, ctx->s_k));
+            TANW_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
+        }
         std::sort(sv.long_list, sv.long_list + sv.n_long);
         for (int i = 0; i < sv.n_long; ++i) {
             LongPair lp;
@@ -820,8 +883,25 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     ta.hist = (int *)ctx->d_hist.p;
     ta.classes = (LineClasses *)ctx->d_classes.p;
     ctx->ta = ta;
-    ctx->table_launches = n_tiles > 0 ? 1 : 0;
+    ctx->table_launches = (n_tiles > 0 && !host_tables) ? 1 : 0;
+    ctx->timing.table_launches = ctx->table_launches;
     for (int c = 0; c < S; ++c) ctx->chunk[c].tables_built = false;
+    if (host_tables) {
+        TANW_CUDA(ctx, cudaEventSynchronize(ctx->ev_small));           // the staging buffer's previous upload (if any) has left
+        PairDesc *pd = reinterpret_cast<PairDesc *>(ctx->h_small);
+        uint8_t *rt = ctx->h_small + (size_t)kHostSurveyPairs * sizeof(PairDesc);
+        int64_t at = 0;
+        for (int64_t p = 0; p < P; ++p) {
+            pd[p].t_off = in.t_off[p]; pd[p].o_off = in.o_off[p]; pd[p].ops_off = at;
+            pd[p].n = in.n[p]; pd[p].m = in.m[p];
+            rt[p] = (uint8_t)kRouteLong;
+            at += (int64_t)in.n[p] + in.m[p];
+        }
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs.p, pd, sizeof(PairDesc) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_k));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_route.p, rt, (size_t)P, cudaMemcpyHostToDevice, ctx->s_k));
+        TANW_CUDA(ctx, cudaEventRecord(ctx->ev_small, ctx->s_k));
+        for (int c = 0; c < S; ++c) ctx->chunk[c].tables_built = true;
+    }
     if (!in.pipelined)
         for (int c = 0; c < S; ++c)
             if (int rc = build_chunk_tables(ctx, c)) return rc;
@@ -1168,7 +1248,7 @@ int tanw_create(int device, tanw_ctx **out)
     cudaEvent_t *evs[] = { &ctx->ev_h2d0, &ctx->ev_h2d1, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_d2h0, &ctx->ev_d2h1 };
     for (auto ev : evs)
         if (e == cudaSuccess) e = cudaEventCreate(ev);
-    cudaEvent_t *plain[] = { &ctx->ev_tab, &ctx->ev_survey, &ctx->ev_idle };
+    cudaEvent_t *plain[] = { &ctx->ev_tab, &ctx->ev_survey, &ctx->ev_idle, &ctx->ev_small };
     for (auto ev : plain)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     for (int i = 0; i < kPieces; ++i)
@@ -1190,6 +1270,7 @@ int tanw_create(int device, tanw_ctx **out)
     }
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_survey, sizeof(Survey));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_misc, 256);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_small, (size_t)kHostSurveyPairs * (sizeof(PairDesc) + 8));
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_idle, ctx->s_k);
     if (e != cudaSuccess) {
         int rc = fail(nullptr, TANW_E_CUDA, "context setup on device %d: %s", device, cudaGetErrorString(e));
@@ -1225,7 +1306,7 @@ int tanw_destroy(tanw_ctx *ctx)
                        &ctx->d_subst, &ctx->d_chain, &ctx->d_ck, &ctx->d_kparams, &ctx->d_sidx, &ctx->d_misc, &ctx->d_pack };
     for (auto b : bufs) b->release();
     cudaEvent_t evs[] = { ctx->ev_h2d0, ctx->ev_h2d1, ctx->ev_k0, ctx->ev_k1, ctx->ev_d2h0, ctx->ev_d2h1,
-                          ctx->ev_tab, ctx->ev_survey, ctx->ev_idle };
+                          ctx->ev_tab, ctx->ev_survey, ctx->ev_idle, ctx->ev_small };
     for (auto ev : evs)
         if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_piece)
@@ -1247,6 +1328,7 @@ int tanw_destroy(tanw_ctx *ctx)
 #endif
     if (ctx->h_survey) cudaFreeHost(ctx->h_survey);
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->h_subst) cudaFreeHost(ctx->h_subst);
     if (ctx->h_kparams) cudaFreeHost(ctx->h_kparams);
     for (auto s : streams)

@@ -85,7 +85,7 @@ struct TableArgs {
 
 constexpr int kHistStride = 2 * kLineKeys + kPageKeys;
 
-__device__ __forceinline__ int route_of(const TableArgs &a, long long np, long long mp)
+__host__ __device__ __forceinline__ int route_of(const TableArgs &a, long long np, long long mp)
 {
     const bool oversize = np > 0 && mp > 0 &&
                           (ptr_bytes((int)np, (int)mp) + 255) / 256 * 256 * kWarpsPerBlock > a.slot_limit &&
