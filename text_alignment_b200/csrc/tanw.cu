@@ -519,7 +519,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     }
     TANW_ENTER(ctx);
 
-    // ---- uploads: pair arrays first (the survey needs only them), then the symbols in pieces ----
+    // ---- uploads: pair arrays first (the survey needs only them; below), then the symbols in pieces ----
     const size_t Pz = (size_t)std::max<int64_t>(P, 1);
     const int64_t n_tiles = (P + kTile - 1) / kTile;
     if (ctx->d_n.reserve(sizeof(int) * Pz) != cudaSuccess || ctx->d_m.reserve(sizeof(int) * Pz) != cudaSuccess ||
@@ -535,18 +535,6 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_idle, 0));
     TANW_CUDA(ctx, cudaEventRecord(ctx->ev_h2d0, ctx->s_in));
     int64_t h2d = 0;
-    if (P > 0) {
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_n.p, in.n, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_m.p, in.m, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_toff.p, in.t_off, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_ooff.p, in.o_off, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-        h2d += 24 * P;
-        if (multi) {
-            TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sidx.p, in.sidx, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-            h2d += 4 * P;
-        }
-    }
-    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_tab, ctx->s_in));
     const int64_t sym_bytes_total = in.symbols_len * sb;
     const int64_t piece_bytes = std::max<int64_t>((sym_bytes_total + kPieces - 1) / kPieces / 256 * 256 + 256, 1 << 16);
 
@@ -580,6 +568,18 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     // ... and when every one of them takes the chained-stripe path (a single page per call), the host
     // writes their descriptors too: no survey and no table kernels at all
     const bool host_tables = host_sv && P > 0 && sv.bad == 0 && sv.n_long == P && !ctx->packed_ops;
+    if (P > 0 && !host_tables) {                         // (an all-chained handful of pairs needs none of them on the device)
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_n.p, in.n, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_m.p, in.m, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_toff.p, in.t_off, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_ooff.p, in.o_off, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        h2d += 24 * P;
+        if (multi) {
+            TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sidx.p, in.sidx, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+            h2d += 4 * P;
+        }
+    }
+    TANW_CUDA(ctx, cudaEventRecord(ctx->ev_tab, ctx->s_in));
     TANW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_tab, 0));
     if (!host_tables) {
         TANW_CUDA(ctx, cudaMemsetAsync(ctx->d_survey.p, 0, survey_head, ctx->s_k));
