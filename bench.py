@@ -53,7 +53,9 @@ def source_digest():
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, 'text_alignment_b200', 'csrc')
     for name in sorted(os.listdir(csrc)):
-        if name.endswith(('.cu', '.cuh', '.h')):
+        # the device code: kernel headers and the per-family translation units (not the host side
+        # of the ABI, tanw.cu, nor the host-only consumer)
+        if name.endswith('.cuh') or name in ('tanw_pairs.cu', 'tanw_lines.cu', 'tanw_long.cu', 'tanw_launch.h'):
             with open(os.path.join(csrc, name), 'rb') as f:
                 h.update(f.read())
     return h.hexdigest()[:16]

@@ -619,6 +619,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         }
     }
     if (!host_sv) TANW_CUDA(ctx, cudaEventSynchronize(ctx->ev_survey));
+    else if (!in.pipelined && !host_tables) TANW_CUDA(ctx, cudaEventSynchronize(ctx->ev_tab));   // tanw.h: the pair arrays are consumed before prepare returns
 
     if (sv.bad != 0) {
         const int64_t p = (int64_t)(0xFFFFFFFFFFFFFFFFull - sv.bad);
