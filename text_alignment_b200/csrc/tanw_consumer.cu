@@ -138,7 +138,20 @@ int syllabify_word_bytes(const char *w, int len, int *out_len)
     Unit *cur = a, *nxt = b;
     int n = 1;
     cur[0] = { 0, len, false, false };
+    // Units are pieces of the word, so a cluster that occurs nowhere in the word cuts nothing: one
+    // look at the word's letter pairs says which of the 21 passes can do anything (usually 0-2).
+    struct PairTable {
+        int8_t idx[128][128];
+        PairTable() { memset(idx, -1, sizeof idx); for (int p = 0; p < kPatterns; ++p) idx[(int)kClusters[p][0]][(int)kClusters[p][1]] = (int8_t)p; }
+    };
+    static const PairTable table;
+    unsigned present = 0;
+    for (int q = 0; q + 1 < len; ++q) {
+        const unsigned char c0 = (unsigned char)w[q], c1 = (unsigned char)w[q + 1];
+        if (c0 < 128 && c1 < 128 && table.idx[c0][c1] >= 0) present |= 1u << table.idx[c0][c1];
+    }
     for (int p = 0; p < kPatterns; ++p) {
+        if (!(present >> p & 1u)) continue;
         const char c0 = kClusters[p][0], c1 = kClusters[p][1];
         int k = 0;
         for (int u = 0; u < n; ++u) {
