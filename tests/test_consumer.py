@@ -57,6 +57,33 @@ def test_abbreviation_expansion_golden(golden):
         assert ''.join(c.char for c in chars) == page['expanded_ocr']
 
 
+def test_abbreviation_expansion_on_arrays_equals_the_object_path():
+    """expand_abbreviations_arrays (string surgery, search resumed near the last replacement) against
+    the object path that follows alignToOCR.py:251-264 literally, and against its own list form:
+    texts dense in abbreviations, adjacent and nested candidates, user-supplied tables whose
+    expansions create new occurrences."""
+    import numpy as np
+    rng = random.Random(5)
+    tables = [None,
+              {'ab': ['b', 'a'], 'bb': ['ab']},                    # an expansion re-creates a key to its left
+              {'aa': ['a'], 'ba': ['a', 'b']},
+              {'x': ['yy'], 'yyy': ['x', 'z', 'y']}]
+    alphabets = ['dnsūealā^ēō l', 'ab', 'ab', 'xyz']
+    for table, alpha in zip(tables, alphabets):
+        for _ in range(150):
+            text = ''.join(rng.choice(alpha) for _ in range(rng.randint(0, 60)))
+            boxes = np.array([[i, 2 * i, i + 5, 2 * i + 7] for i in range(len(text))], dtype=np.int32).reshape(-1, 4)
+            kw = {} if table is None else {'abbreviations': table}
+            got_s, got_b = atocr.expand_abbreviations_arrays(text, boxes, **kw)
+            lst_s, lst_b = atocr._expand_abbreviations_arrays_lists(text, boxes, table or latsyl.abbreviations)
+            chars = atocr.expand_abbreviations([atocr.CharBox(c, (int(b[0]), int(b[1])), (int(b[2]), int(b[3])))
+                                                for c, b in zip(text, boxes)], **kw)
+            assert got_s == lst_s == ''.join(c.char for c in chars)
+            want = np.array([[c.ulx, c.uly, c.lrx, c.lry] for c in chars], dtype=np.int32).reshape(-1, 4)
+            assert np.array_equal(np.asarray(got_b).reshape(-1, 4), want)
+            assert np.array_equal(np.asarray(lst_b).reshape(-1, 4), want)
+
+
 def test_abbreviation_boxes_inherit_from_source_character():
     chars = [atocr.CharBox(c, (10 * k, 0), (10 * k + 9, 5)) for k, c in enumerate('a dns b')]
     out = atocr.expand_abbreviations(chars)

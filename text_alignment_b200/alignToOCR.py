@@ -217,7 +217,7 @@ def syllable_spans(transcript):
     the regular-expression path)."""
     bounds = _native.syllable_bounds(transcript)
     if bounds is not None:                                   # the native syllabifier (ASCII text)
-        return [transcript[a:b] for a, b in bounds.tolist()], bounds
+        return [transcript[a:b] for a, b in zip(bounds[:, 0].tolist(), bounds[:, 1].tolist())], bounds
     words = transcript.split(' ')
     per_word = [_word_syllables(w) for w in words]
     syls = [s for ws in per_word for s in ws]
@@ -240,8 +240,50 @@ def syllable_spans(transcript):
 def expand_abbreviations_arrays(ocr, boxes, abbreviations=None):
     """alignToOCR.py:251-264 on (OCR string, boxes int32[k, 4]): same replacements in the same
     order as ``expand_abbreviations``; every expanded letter inherits the box of the abbreviation
-    character its segment stands for."""
+    character its segment stands for.
+
+    Which box a character uses is carried in a second STRING (character i = chr(box index)), so
+    that the reference's list surgery (two slices and a concatenation of the whole page per
+    occurrence) becomes string slicing, a memcpy.  After a replacement at ``idx`` the next leftmost
+    occurrence cannot lie wholly left of ``idx - len(abb) + 1`` (it would have been found first),
+    so the search resumes there instead of at 0 -- the same occurrences in the same order."""
     abbreviations = latsyl.abbreviations if abbreviations is None else abbreviations
+    if len(ocr) >= 0xD000:                      # box indices must stay below the surrogate range
+        return _expand_abbreviations_arrays_lists(ocr, boxes, abbreviations)
+    src = None
+    for abb, segments in abbreviations.items():
+        if not abb:
+            continue
+        start = 0
+        ins = ''.join(segments)
+        while True:
+            idx = ocr.find(abb, start)
+            if idx == -1:
+                break
+            if src is None:
+                src = _identity_string(len(ocr))
+            ins_src = ''.join([src[idx + i] * len(seg) for i, seg in enumerate(segments)])
+            ocr = ocr[:idx] + ins + ocr[idx + len(abb):]
+            src = src[:idx] + ins_src + src[idx + len(abb):]
+            start = max(0, idx - len(abb) + 1)
+    if src is None:
+        return ocr, boxes
+    index = np.frombuffer(src.encode('utf-32-le'), dtype=np.uint32).astype(np.intp)
+    return ocr, np.ascontiguousarray(np.asarray(boxes, dtype=np.int32).reshape(-1, 4)[index])
+
+
+_IDENTITY = ['']
+
+
+def _identity_string(k):
+    """chr(0) chr(1) ... chr(k-1): built once, sliced afterwards."""
+    if len(_IDENTITY[0]) < k:
+        _IDENTITY[0] = ''.join(map(chr, range(max(k, 4096))))
+    return _IDENTITY[0][:k]
+
+
+def _expand_abbreviations_arrays_lists(ocr, boxes, abbreviations):
+    """The same with a list of box indices (pages too long for the string form)."""
     src = None                                  # index of the box each current character uses
     for abb, segments in abbreviations.items():
         while True:
