@@ -131,6 +131,8 @@ def pylist():
             lib.tanw_pylist_expand.restype = ctypes.py_object
             lib.tanw_pylist_expand.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_int,
                                                ctypes.py_object]
+            lib.tanw_pylist_slices.restype = ctypes.py_object
+            lib.tanw_pylist_slices.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_void_p]
             _pylist = lib
         except (OSError, AttributeError):
             _pylist = False
@@ -163,6 +165,20 @@ def _consumer_check(rc):
         if 'all_chars not same length' in msg:
             raise AssertionError(msg)          # the reference's own assertion (alignToOCR.py:291)
         raise ValueError(msg)
+
+
+def text_slices(text, bounds, keep=None):
+    """[text[a:b] for a, b in bounds] (only where ``keep`` is set, if given) -- through the CPython
+    helper when it is built, else in Python."""
+    bounds = np.ascontiguousarray(bounds, dtype=np.int32).reshape(-1, 2)
+    lib = pylist()
+    if lib is not None and type(text) is str:
+        k = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+        return lib.tanw_pylist_slices(text, bounds.ctypes.data, bounds.shape[0], None if k is None else k.ctypes.data)
+    rows = zip(bounds[:, 0].tolist(), bounds[:, 1].tolist())
+    if keep is None:
+        return [text[a:b] for a, b in rows]
+    return [text[a:b] for (a, b), h in zip(rows, np.asarray(keep).tolist()) if h]
 
 
 def syllable_bounds(text):

@@ -210,14 +210,14 @@ def regex_free(transcript):
     return body == '' or body.isalnum()
 
 
-def syllable_spans(transcript):
+def syllable_spans(transcript, strings=True):
     """-> (syllables, bounds int32[S, 2]): syllable s is transcript[bounds[s, 0]:bounds[s, 1]].
     Words are what ``split(' ')`` gives (latinSyllabification.py:171); a word's syllables are
     consecutive pieces of it (None is returned if that ever fails to hold, and the caller keeps
     the regular-expression path)."""
     bounds = _native.syllable_bounds(transcript)
     if bounds is not None:                                   # the native syllabifier (ASCII text)
-        return [transcript[a:b] for a, b in zip(bounds[:, 0].tolist(), bounds[:, 1].tolist())], bounds
+        return (_native.text_slices(transcript, bounds) if strings else None), bounds
     words = transcript.split(' ')
     per_word = [_word_syllables(w) for w in words]
     syls = [s for ws in per_word for s in ws]
@@ -326,7 +326,7 @@ def boxes_for_pages_arrays(pages, seq_align_params=None, devices=None):
     results = [None] * len(pages)
     fast = []
     for k, (transcript, ocr, boxes) in enumerate(pages):
-        spans = syllable_spans(transcript) if regex_free(transcript) else None
+        spans = syllable_spans(transcript, strings=False) if regex_free(transcript) else None
         if spans is None:
             chars = [CharBox(c, (int(b[0]), int(b[1])), (int(b[2]), int(b[3]))) for c, b in zip(ocr, np.asarray(boxes).reshape(-1, 4))]
             syl_boxes = boxes_for_page(transcript, chars, seq_align_params, device=(devices or [0])[0])[0]
@@ -343,10 +343,14 @@ def boxes_for_pages_arrays(pages, seq_align_params=None, devices=None):
         np.cumsum([f[3].shape[0] for f in fast], out=box_off[1:])
         out, has = _native.syllable_boxes(ops, ops_off, ops_len, np.concatenate([f[4][1] for f in fast]), syl_off,
                                           np.concatenate([f[3] for f in fast]), box_off)
-        for j, (k, _, _, _, (syls, _)) in enumerate(fast):
+        for j, (k, transcript, _, _, (syls, bounds)) in enumerate(fast):
             lo, hi = int(syl_off[j]), int(syl_off[j + 1])
             keep = has[lo:hi]
-            results[k] = ([s for s, h in zip(syls, keep.tolist()) if h], out[lo:hi][keep])
+            if syls is None:                      # the native syllabifier's ranges: only the kept syllables become strings
+                kept = _native.text_slices(transcript, bounds, keep=keep)
+            else:
+                kept = [s for s, h in zip(syls, keep.tolist()) if h]
+            results[k] = (kept, out[lo:hi][keep])
     return results
 
 

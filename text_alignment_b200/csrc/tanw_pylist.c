@@ -67,3 +67,39 @@ PyObject *tanw_pylist_expand(PyObject *src, const uint8_t *ops, Py_ssize_t L, in
     }
     return out;
 }
+
+/* Substrings text[bounds[2i] : bounds[2i+1]] as a new list (the syllables of a transcript,
+ * latinSyllabification.syllabify_text -> alignToOCR.py:277, from the native syllabifier's ranges).
+ * `keep`, when not NULL, selects the ranges to take.  NULL with an exception set on bad ranges. */
+PyObject *tanw_pylist_slices(PyObject *text, const int32_t *bounds, Py_ssize_t count, const uint8_t *keep)
+{
+    if (!PyUnicode_CheckExact(text)) {
+        PyErr_SetString(PyExc_TypeError, "tanw_pylist_slices: text must be a str");
+        return NULL;
+    }
+    const Py_ssize_t len = PyUnicode_GET_LENGTH(text);
+    Py_ssize_t kept = count;
+    if (keep) {
+        kept = 0;
+        for (Py_ssize_t i = 0; i < count; ++i) kept += keep[i] != 0;
+    }
+    PyObject *out = PyList_New(kept);
+    if (!out) return NULL;
+    Py_ssize_t at = 0;
+    for (Py_ssize_t i = 0; i < count; ++i) {
+        if (keep && !keep[i]) continue;
+        const Py_ssize_t a = bounds[2 * i], b = bounds[2 * i + 1];
+        if (a < 0 || b < a || b > len) {
+            Py_DECREF(out);
+            PyErr_SetString(PyExc_ValueError, "tanw_pylist_slices: range outside the text");
+            return NULL;
+        }
+        PyObject *piece = PyUnicode_Substring(text, a, b);
+        if (!piece) {
+            Py_DECREF(out);
+            return NULL;
+        }
+        PyList_SET_ITEM(out, at++, piece);
+    }
+    return out;
+}
