@@ -127,6 +127,7 @@ struct tanw_ctx {
     Survey *h_survey = nullptr;           // pinned: the device's report on the batch
     int *h_misc = nullptr;                // pinned: [0] device assertion word, [1] largest symbol code
     uint8_t *h_small = nullptr;           // pinned: pair descriptors + routes of a handful of pairs built by the host
+    uint8_t *h_io = nullptr;              // pinned: inputs / results of a small batch travel through here (kSmallIo bytes each way)
     int *h_subst = nullptr;               // pinned copy of the substitution table in kernel encoding
     size_t h_subst_cap = 0;
     KParams *h_kparams = nullptr;         // pinned: per-pair scoring systems of a multi batch
@@ -447,6 +448,10 @@ struct PrepareInput {
 // pattern (alignToOCR.py:273); waiting for the device's report and then for its list of
 // chained-stripe pairs costs two round trips of ~30 us each, a sixth of such a call.
 constexpr int64_t kHostSurveyPairs = 64;
+// A small batch -- one page per call is the reference's own pattern -- is copied through page-locked
+// staging of the context: a caller's ordinary (pageable) memory makes every cudaMemcpyAsync a
+// synchronous, separately staged transfer, ~10 us apiece for a dozen copies of a few bytes.
+constexpr int64_t kSmallIo = 128 << 10;
 void host_survey(const TableArgs &a, const PrepareInput &in, Survey &sv)
 {
     memset(&sv, 0, offsetof(Survey, long_list));
@@ -568,11 +573,28 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
     // ... and when every one of them takes the chained-stripe path (a single page per call), the host
     // writes their descriptors too: no survey and no table kernels at all
     const bool host_tables = host_sv && P > 0 && sv.bad == 0 && sv.n_long == P && !ctx->packed_ops;
+    // small inputs go through the context's page-locked staging (its previous use has left: the
+    // stream has passed ev_h2d1 of the previous batch)
+    const uint8_t *sym_src = in.symbols;
+    const int32_t *n_src = in.n, *m_src = in.m;
+    const int64_t *t_src = in.t_off, *o_src = in.o_off;
+    if (host_sv && sym_bytes_total + 24 * P <= kSmallIo) {
+        TANW_CUDA(ctx, cudaEventSynchronize(ctx->ev_h2d1));
+        uint8_t *at = ctx->h_io;
+        auto put = [&at](const void *src, size_t bytes) { uint8_t *p = at; if (bytes) memcpy(p, src, bytes); at += (bytes + 15) / 16 * 16; return p; };
+        if (P > 0 && !host_tables) {
+            t_src = (const int64_t *)put(in.t_off, sizeof(int64_t) * (size_t)P);
+            o_src = (const int64_t *)put(in.o_off, sizeof(int64_t) * (size_t)P);
+            n_src = (const int32_t *)put(in.n, sizeof(int32_t) * (size_t)P);
+            m_src = (const int32_t *)put(in.m, sizeof(int32_t) * (size_t)P);
+        }
+        sym_src = put(in.symbols, (size_t)sym_bytes_total);
+    }
     if (P > 0 && !host_tables) {                         // (an all-chained handful of pairs needs none of them on the device)
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_n.p, in.n, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_m.p, in.m, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_toff.p, in.t_off, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
-        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_ooff.p, in.o_off, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_n.p, n_src, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_m.p, m_src, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_toff.p, t_src, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
+        TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_ooff.p, o_src, sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
         h2d += 24 * P;
         if (multi) {
             TANW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sidx.p, in.sidx, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, ctx->s_in));
@@ -598,7 +620,7 @@ int prepare_impl(tanw_ctx *ctx, const PrepareInput &in)
         const int64_t lo = std::min(sym_bytes_total, piece_bytes * i), hi = std::min(sym_bytes_total, piece_bytes * (i + 1));
         if (hi <= lo && i > 0) break;                   // a chunk waits for the piece its last symbol is in: never an empty one
         if (hi > lo)
-            TANW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_sym.p + lo, in.symbols + lo, (size_t)(hi - lo),
+            TANW_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_sym.p + lo, sym_src + lo, (size_t)(hi - lo),
                                            cudaMemcpyHostToDevice, ctx->s_in));
         TANW_CUDA(ctx, cudaEventRecord(ctx->ev_piece[i], ctx->s_in));
     }
@@ -1089,6 +1111,18 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
         }
         dst = ctx->h_stage.data();
     }
+    // small results come back through the context's page-locked staging (see kSmallIo)
+    const int64_t ops_bytes = packed ? ctx->ops_total / 4 + P + 1 : ctx->ops_total;
+    const int64_t ops_room = (ops_bytes + 15) / 16 * 16, len_room = (4 * P + 15) / 16 * 16;
+    const bool small_out = canonical && P <= kHostSurveyPairs && ops_room + len_room + 12 * P + 16 <= kSmallIo;
+    uint8_t *const user_ops = ops;
+    int32_t *const user_len = ops_len, *const user_scores = scores;
+    if (small_out) {
+        uint8_t *base = ctx->h_io + kSmallIo;
+        dst = base;
+        ops_len = reinterpret_cast<int32_t *>(base + ops_room);
+        if (scores) scores = reinterpret_cast<int32_t *>(base + ops_room + len_room);
+    }
     int64_t d2h = 0;
     for (int c = 0; c < ctx->n_chunks; ++c) {
         const ChunkPlan &cp = ctx->chunk[c];
@@ -1144,6 +1178,12 @@ int fetch_impl(tanw_ctx *ctx, uint8_t *ops, const int64_t *ops_off, int64_t ops_
 #endif
     if (ctx->h_misc[0] != 0)
         return fail(ctx, TANW_E_INTERNAL, "device assertion %d failed (TANW_CHECKED build)", ctx->h_misc[0]);
+    if (small_out) {
+        if (ops_bytes > 0) memcpy(user_ops, dst, (size_t)ops_bytes);
+        if (P > 0) memcpy(user_len, ops_len, sizeof(int32_t) * (size_t)P);
+        if (user_scores && P > 0) memcpy(user_scores, scores, sizeof(int32_t) * 3 * (size_t)P);
+        ops_len = user_len;
+    }
     if (!canonical) {
         int64_t at = 0;
         for (int64_t p = 0; p < P; ++p) {
@@ -1272,6 +1312,7 @@ int tanw_create(int device, tanw_ctx **out)
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_survey, sizeof(Survey));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_misc, 256);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_small, (size_t)kHostSurveyPairs * (sizeof(PairDesc) + 8));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_io, (size_t)(2 * kSmallIo));
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_idle, ctx->s_k);
     if (e != cudaSuccess) {
         int rc = fail(nullptr, TANW_E_CUDA, "context setup on device %d: %s", device, cudaGetErrorString(e));
@@ -1330,6 +1371,7 @@ int tanw_destroy(tanw_ctx *ctx)
     if (ctx->h_survey) cudaFreeHost(ctx->h_survey);
     if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->h_io) cudaFreeHost(ctx->h_io);
     if (ctx->h_subst) cudaFreeHost(ctx->h_subst);
     if (ctx->h_kparams) cudaFreeHost(ctx->h_kparams);
     for (auto s : streams)
