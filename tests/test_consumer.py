@@ -84,6 +84,28 @@ def test_abbreviation_expansion_on_arrays_equals_the_object_path():
             assert np.array_equal(np.asarray(lst_b).reshape(-1, 4), want)
 
 
+def test_text_slices_helper_and_python_fallback(monkeypatch):
+    """_native.text_slices: the CPython helper (csrc/tanw_pylist.c) and the pure-Python form give
+    the same lists, with and without a keep mask; a range outside the text is an error."""
+    import numpy as np
+    from text_alignment_b200 import _native
+    text = 'kyrieeleisonā ē'
+    bounds = np.array([[0, 2], [2, 5], [5, 5], [5, 12], [12, 13], [14, 15]], dtype=np.int32)
+    keep = np.array([1, 0, 1, 1, 0, 1], dtype=np.uint8)
+    want_all = [text[a:b] for a, b in bounds.tolist()]
+    want_kept = [w for w, h in zip(want_all, keep.tolist()) if h]
+    assert _native.text_slices(text, bounds) == want_all
+    assert _native.text_slices(text, bounds, keep=keep) == want_kept
+    assert _native.text_slices(text, bounds, keep=keep.astype(bool)) == want_kept
+    assert _native.text_slices('', np.zeros((0, 2), np.int32)) == []
+    if _native.pylist() is not None:
+        with pytest.raises(ValueError):
+            _native.text_slices('abc', np.array([[1, 9]], dtype=np.int32))
+    monkeypatch.setattr(_native, 'pylist', lambda: None)
+    assert _native.text_slices(text, bounds) == want_all
+    assert _native.text_slices(text, bounds, keep=keep) == want_kept
+
+
 def test_abbreviation_boxes_inherit_from_source_character():
     chars = [atocr.CharBox(c, (10 * k, 0), (10 * k + 9, 5)) for k, c in enumerate('a dns b')]
     out = atocr.expand_abbreviations(chars)
